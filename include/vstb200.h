@@ -1,0 +1,140 @@
+/*
+ * vstb200.h — C ABI of libvstb200.so: the B200-native (sm_100a) CAP-VSTNet stylization hot path.
+ *
+ * The reference (delldu/VSTNet) is pure eager PyTorch and has no native/FFI interface for this
+ * path; the "interface each entry point replaces" is therefore the reference's Python call site
+ * (file:line cited per function, relative to the reference root).  Host code (Python, ctypes —
+ * see INTEGRATION.md) passes raw device pointers, integer shapes and a CUDA stream handle.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; vst_last_error() then returns a
+ *    thread-local, human-readable message.  No C++ exceptions cross this boundary.
+ *  - all device memory is owned by the caller (torch); the library never allocates or frees device
+ *    memory and never synchronises the device.  Work is enqueued on `stream` (a cudaStream_t /
+ *    CUstream passed as void*; NULL = legacy default stream).
+ *  - feature maps are fp32, NCHW, contiguous.  Masks are uint8 [H*W] label maps, labels 0..254.
+ */
+#ifndef VSTB200_H
+#define VSTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VST_MAX_STAGES 8
+#define VST_MAX_LABELS 256 /* uint8 labels; the reference sizes its table max(label)+1 (cWCT.py:173-175) */
+#define VST_MAX_STYLES 16
+
+/* -------------------------------------------------------------------------------------------
+ * Library
+ * ----------------------------------------------------------------------------------------- */
+const char* vst_last_error(void);
+int vst_version(void);
+/* number of device kernels this library has launched in the calling process (for bench.py's
+ * "gpu_launches" and for tests that prove the CUDA path ran). */
+unsigned long long vst_launch_count(void);
+
+/* -------------------------------------------------------------------------------------------
+ * RevResNet  — replaces models/RevResNet.py:166-239 (class RevResNet, _forward, _inverse),
+ *              :68-116 (residual_block), :119-163 (channel_reduction), :19-43 (pad / squeeze).
+ * ----------------------------------------------------------------------------------------- */
+typedef struct vst_revnet_config {
+    int n_stages;                 /* len(nBlocks)                       RevResNet.py:168 */
+    int n_blocks[VST_MAX_STAGES]; /* nBlocks                            RevResNet.py:168 */
+    int n_strides[VST_MAX_STAGES];/* nStrides (1 or 2)                  RevResNet.py:169 */
+    int n_channels[VST_MAX_STAGES];/* nChannels (half-state channels)   RevResNet.py:170 */
+    int in_channel;               /* 3                                  RevResNet.py:171 */
+    int mult;                     /* bottleneck divisor, 4              RevResNet.py:172 */
+    int hidden_dim;               /* 16 photorealistic / 64 artistic    RevResNet.py:173 */
+    int sp_steps;                 /* 2 photorealistic / 1 artistic      RevResNet.py:174 */
+    int n_cr_blocks;              /* channel_reduction n_blocks, 2      RevResNet.py:120 */
+} vst_revnet_config;
+
+typedef struct vst_revnet vst_revnet; /* host-side plan; holds no device memory */
+
+/* precision of the convolution arithmetic */
+#define VST_CONV_FP32 0     /* CUDA-core FFMA, fp32 exact products                          */
+#define VST_CONV_TF32X3 1   /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-equivalent) */
+#define VST_CONV_TF32X2 2   /* tcgen05 kind::tf32, activations split hi+lo, weights rounded to tf32 */
+#define VST_CONV_TF32 3     /* tcgen05 kind::tf32, single term                              */
+
+int vst_revnet_create(const vst_revnet_config* cfg, vst_revnet** out);   /* RevResNet.__init__ :167-190 */
+void vst_revnet_destroy(vst_revnet* net);
+int vst_revnet_set_precision(vst_revnet* net, int mode);
+int vst_revnet_latent_channels(const vst_revnet* net);                    /* 2*hidden_dim */
+int vst_revnet_down_scale(const vst_revnet* net);                         /* prod(nStrides), RevResNet.py:186 */
+
+/* Raw parameters: ONE flat fp32 device buffer holding the reference's state_dict tensors in
+ * state_dict order (stack.{i}.conv.{1,4,7}.{weight,bias}, then
+ * channel_reduction.block_list.{j}.conv.{1,4,7}.{weight,bias}), each OIHW contiguous
+ * (SURVEY.md A.2).  vst_revnet_pack_weights repacks them on the device into the kernels'
+ * layouts (incl. the hi/lo tf32 split); `packed` must have vst_revnet_packed_bytes() bytes. */
+size_t vst_revnet_param_floats(const vst_revnet* net);
+size_t vst_revnet_packed_bytes(const vst_revnet* net);
+int vst_revnet_pack_weights(const vst_revnet* net, const float* raw_params, void* packed, void* stream);
+
+/* scratch needed by forward / inverse for a B x 3 x H x W image (H, W multiples of down_scale) */
+size_t vst_revnet_workspace_bytes(const vst_revnet* net, int B, int H, int W);
+
+/* encode: x [B,in_channel,H,W] -> z [B, 2*hidden_dim, H*2^sp/ds, W*2^sp/ds]
+ * replaces RevResNet.forward(x, forward=True) (RevResNet.py:203-223). */
+int vst_revnet_forward(const vst_revnet* net, const void* packed, const float* x, float* z,
+                       int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+/* decode: z -> x [B,in_channel,H,W]; z is not modified.
+ * replaces RevResNet.forward(z, forward=False) (RevResNet.py:225-239). */
+int vst_revnet_inverse(const vst_revnet* net, const void* packed, const float* z, float* x,
+                       int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * cWCT — replaces models/cWCT.py: whitening :134-149, coloring :152-164, cholesky_dec :111-132,
+ *        _transfer :24-47, _transfer_seg :49-109, compute_label_info :166-189, interpolation
+ *        :206-262.   out = T_l (x - mu_c,l) + beta_l per label l.
+ * ----------------------------------------------------------------------------------------- */
+
+/* A "stats" block describes the first and second moments of one feature map, per label:
+ *   count [L] (double), sum [L*C] (double), gram [L*C*C] (double, sum of (x-p)(x-p)^T with the
+ *   per-channel pivot p [C] (float) chosen by the library to avoid cancellation).
+ * vst_cwct_stats_bytes gives the size of one block; layout is private to the library. */
+size_t vst_cwct_stats_bytes(int C, int n_labels);
+
+/* feat [C, n] fp32 (one sample), labels uint8 [n] or NULL (=> one label, 0; n_labels must be 1).
+ * Replaces the mean / centre / x@x.T of cWCT.py:138-144, :153-157 and the per-label
+ * np.where + index_select of :87-95.  Zero-initialises `stats` itself. */
+int vst_cwct_stats(const float* feat, int C, long long n, const uint8_t* labels, int n_labels,
+                   void* stats, void* stream);
+
+/* Per label: covariance (n-1 divisor), Cholesky with the cumulative eps*I retry (cWCT.py:111-128),
+ * triangular solve, T = (1-alpha_c) * (sum_k alpha_s[k] Ls_k) Lc^-1 + alpha_c I,
+ * mu = mu_c,  beta = (1-alpha_c) sum_k alpha_s[k] mu_s,k + alpha_c mu_c   (out = T (x - mu) + beta).
+ * masked != 0 applies the validity rule of cWCT.py:178 (n_c>10, n_s>10, ratios < 100) per label;
+ * invalid labels get T = I, mu = beta = 0 and valid[l] = 0.
+ *   T [L,C,C] fp32, mu [L,C] fp32, beta [L,C] fp32, valid [L] int32, status [L] int32 (#jitter
+ *   retries, <0 on failure).  use_double selects fp64 factor arithmetic (cWCT.py:13 use_double); otherwise the
+ *   covariance is rounded to fp32 first, as the reference's fp32 matmul result would be. */
+int vst_cwct_factor(const void* content_stats, const void* const* style_stats, const float* alpha_s,
+                    int n_styles, float alpha_c, float eps, int C, int n_labels, int masked,
+                    int use_double, float* T, float* mu, float* beta, int* valid, int* status, void* stream);
+
+/* out[:,p] = T[l(p)] (feat[:,p] - mu[l(p)]) + beta[l(p)]; labels NULL => l = 0; pixels whose
+ * label has valid[l] == 0 are copied through.  `out` may alias `feat`.
+ * Replaces inv_L @ x, Ls @ whiten + mean (cWCT.py:147,161-162,256-257) and the index_copy_
+ * scatter of :99-101. */
+int vst_cwct_apply(const float* feat, float* out, int C, long long n, const uint8_t* labels,
+                   int n_labels, const float* T, const float* mu, const float* beta, const int* valid,
+                   void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Frame I/O helpers for the video entry point (video_transfer.py:188, :211-214).
+ * ----------------------------------------------------------------------------------------- */
+/* uint8 HWC (RGB or BGR) -> fp32 CHW RGB in [0,1]  (ToTensor, video_transfer.py:188) */
+int vst_frame_u8_to_f32(const uint8_t* hwc, float* chw, int H, int W, int bgr, void* stream);
+/* fp32 CHW -> uint8 HWC, mul(255).clamp(0,255).byte() truncation (video_transfer.py:211-214) */
+int vst_frame_f32_to_u8(const float* chw, uint8_t* hwc, int H, int W, int bgr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSTB200_H */

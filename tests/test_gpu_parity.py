@@ -1,0 +1,214 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against (a) the golden vectors
+recorded from the reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances (written here, per the task statement): stylized pixels max-abs <= 1e-3; the
+RevResNet round trip must be no worse than the reference's own on the same input; individual
+ops are held to much tighter bounds so a regression shows up early.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vst_oracle as O
+from tests.helpers import MODES, blocky_mask, build_net, cpu_state_dict, load_golden, rand_img
+
+pytestmark = pytest.mark.gpu
+
+PIXEL_TOL = 1e-3
+OP_TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def maxdiff(a, b):
+    return float((a.detach().cpu().double() - torch.as_tensor(b).double()).abs().max())
+
+
+@pytest.mark.parametrize("mode", ["photo", "art"])
+@pytest.mark.parametrize("bias_seed", [None, 7])
+def test_revnet_vs_golden(dev, mode, bias_seed):
+    from vstnet_b200 import _lib
+    g = load_golden("revnet_%s_b%s.npz" % (mode, "0" if bias_seed is None else bias_seed))
+    net = build_net(mode, 0, bias_seed).to(dev)
+    n0 = _lib.launch_count()
+    z = net(torch.from_numpy(g["x"]).to(dev), forward=True)
+    assert _lib.launch_count() - n0 >= 96, "the native conv kernels did not run"
+    assert z.shape == g["z"].shape
+    assert maxdiff(z, g["z"]) <= OP_TOL
+    xd = net(torch.from_numpy(g["z_rand"]).to(dev), forward=False)
+    assert maxdiff(xd, g["x_dec"]) <= OP_TOL
+    xr = net(z, forward=False)
+    assert maxdiff(xr, g["x"]) <= max(float(g["roundtrip_err"]), 3e-7)
+
+
+@pytest.mark.parametrize("mode,h,w,b", [("photo", 40, 72, 1), ("art", 36, 44, 2), ("photo", 8, 8, 1),
+                                        ("photo", 132, 260, 1)])
+def test_revnet_vs_oracle_odd_sizes(dev, mode, h, w, b):
+    net = build_net(mode, 3, 9)
+    sd = cpu_state_dict(net)
+    net = net.to(dev)
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    x = torch.rand(b, 3, h, w, generator=g)
+    with torch.no_grad():
+        zr = O.revnet_forward(sd, x, **MODES[mode])
+        xr_ref = O.revnet_inverse(sd, zr, **MODES[mode])
+    z = net(x.to(dev))
+    assert maxdiff(z, zr) <= OP_TOL
+    xr = net.inverse(z)
+    ref_rt = float((xr_ref - x).abs().max())
+    assert maxdiff(xr, x) <= max(ref_rt, 3e-7), "round trip worse than the reference's own (%g)" % ref_rt
+    assert not z.requires_grad
+
+
+def test_revnet_rejects_bad_shapes(dev):
+    net = build_net("photo").to(dev)
+    with pytest.raises(ValueError):
+        net(torch.rand(1, 3, 30, 32, device=dev))
+    with pytest.raises(ValueError):
+        net(torch.rand(1, 4, 32, 32, device=dev))
+    with pytest.raises(ValueError):
+        net(torch.rand(1, 32, 6, 8, device=dev), forward=False)
+
+
+@pytest.mark.parametrize("C", [32, 128])
+def test_cwct_plain_vs_golden(dev, C):
+    from vstnet_b200 import cWCT
+    g = load_golden("cwct_plain_c%d.npz" % C)
+    zc, zs, zs2 = (torch.from_numpy(g[k]).to(dev) for k in ("zc", "zs", "zs2"))
+    cw = cWCT()
+    tol = 5e-5 if C == 32 else 2e-4
+    zc0 = zc.clone()
+    assert maxdiff(cw.transfer(zc, zs), g["out_a0"]) <= tol
+    assert torch.equal(zc, zc0), "unmasked transfer must not modify its input"
+    assert maxdiff(cw.interpolation(zc, [zs], [1.0], 0.5), g["out_a05"]) <= tol
+    assert maxdiff(cw.interpolation(zc, [zs, zs2], [0.3, 0.7], 0.25), g["out_multi"]) <= tol
+    assert int(cw.last_status.cpu()[0]) == 0          # no jitter retries on a well-conditioned input
+
+
+def test_cwct_masked_vs_golden(dev):
+    from vstnet_b200 import cWCT
+    g = load_golden("cwct_masked_c32.npz")
+    zc, zs = torch.from_numpy(g["zc"]).to(dev), torch.from_numpy(g["zs"]).to(dev)
+    out = cWCT().transfer(zc, zs, g["cmask"], g["smask"])
+    assert out.data_ptr() == zc.data_ptr(), "masked transfer writes into content_feat (ref: cWCT.py:103)"
+    assert maxdiff(out, g["out"]) <= 5e-5
+    keep = torch.from_numpy(g["cmask"][0] == 5)
+    assert torch.equal(out.cpu()[0][:, keep], torch.from_numpy(g["zc"])[0][:, keep]), "invalid label must be identity"
+
+
+def test_cwct_masked_speckled_and_device_masks(dev):
+    """Per-pixel random labels (worst case for the label-run logic) with torch uint8 masks."""
+    from vstnet_b200 import cWCT
+    g = torch.Generator().manual_seed(77)
+    zc = torch.randn(1, 32, 40, 44, generator=g) * 0.5
+    zs = torch.randn(1, 32, 36, 52, generator=g) * 0.3 + 0.2
+    cm = torch.randint(0, 4, (1, 40, 44), generator=g, dtype=torch.uint8)
+    sm = torch.randint(0, 5, (1, 36, 52), generator=g, dtype=torch.uint8)
+    ref = O.cwct_transfer_seg(zc, zs, cm.numpy(), sm.numpy())
+    out = cWCT().transfer(zc.to(dev).clone(), zs.to(dev), cm.to(dev), sm.to(dev))
+    assert maxdiff(out, ref) <= 1e-4
+
+
+def test_cwct_masked_all_ones_equals_unmasked(dev):
+    from vstnet_b200 import cWCT
+    g = torch.Generator().manual_seed(78)
+    zc = (torch.randn(1, 32, 24, 24, generator=g) * 0.5).to(dev)
+    zs = (torch.randn(1, 32, 28, 20, generator=g) * 0.3).to(dev)
+    a = cWCT().transfer(zc, zs)
+    b = cWCT().transfer(zc.clone(), zs, np.ones((1, 24, 24), np.uint8), np.ones((1, 28, 20), np.uint8))
+    assert maxdiff(a, b.cpu()) <= 1e-6
+
+
+def test_cwct_rank_deficient_label_uses_jitter(dev):
+    """n_c=20, n_s=25 < C=32: singular covariances; the reference's Cholesky fails once and succeeds
+    after +eps*I.  Loose tolerance: the outcome depends on rounding noise."""
+    from vstnet_b200 import cWCT
+    g = torch.Generator().manual_seed(79)
+    zc = torch.randn(1, 32, 16, 16, generator=g) * 0.5
+    zs = torch.randn(1, 32, 16, 16, generator=g) * 0.4
+    cm = np.zeros((1, 16, 16), np.uint8)
+    sm = np.zeros((1, 16, 16), np.uint8)
+    cm.reshape(-1)[:20] = 1
+    sm.reshape(-1)[:25] = 1
+    ref = O.cwct_transfer_seg(zc, zs, cm, sm)
+    cw = cWCT()
+    out = cw.transfer(zc.to(dev).clone(), zs.to(dev), cm, sm)
+    st = cw.last_status.cpu().tolist()
+    assert st[0] == 0 and st[1] >= 2, "label 1 should need one jitter retry on each side (got %s)" % st
+    assert maxdiff(out, ref) <= 2e-3
+
+
+def test_cwct_c16_generic_channels(dev):
+    """The reference's own __main__ smoke uses C=16 (cWCT.py:265-283)."""
+    from vstnet_b200 import cWCT
+    g = torch.Generator().manual_seed(80)
+    c = torch.rand(2, 16, 64, 32, generator=g)
+    s_list = [torch.rand(2, 16, 16, 24, generator=g) for _ in range(4)]
+    ref = O.cwct_interpolation(c, s_list, [0.25] * 4, 0.5)
+    out = cWCT().interpolation(c.to(dev), [s.to(dev) for s in s_list], [0.25] * 4, 0.5)
+    assert maxdiff(out, ref) <= 5e-5
+    ref2 = O.cwct_transfer(c, s_list[0])
+    assert maxdiff(cWCT().transfer(c.to(dev), s_list[0].to(dev)), ref2) <= 5e-5
+
+
+@pytest.mark.parametrize("name,mode", [("e2e_photo.npz", "photo"), ("e2e_art.npz", "art")])
+def test_end_to_end_vs_golden(dev, name, mode):
+    from vstnet_b200 import cWCT
+    g = load_golden(name)
+    net = build_net(mode, 0, 7).to(dev)
+    zc, zs = net(torch.from_numpy(g["content"]).to(dev)), net(torch.from_numpy(g["style"]).to(dev))
+    a = float(g["alpha_c"])
+    zcs = cWCT().transfer(zc, zs) if a < 0 else cWCT().interpolation(zc, [zs], [1.0], a)
+    y = net(zcs, forward=False)
+    assert maxdiff(y, g["stylized"]) <= PIXEL_TOL
+    assert maxdiff(y, g["stylized"]) <= 1e-4        # fp32 path: far inside the stated tolerance
+
+
+def test_end_to_end_masked_vs_golden(dev):
+    from vstnet_b200 import cWCT
+    g = load_golden("e2e_photo_masked.npz")
+    net = build_net("photo", 0, 7).to(dev)
+    zc, zs = net(torch.from_numpy(g["content"]).to(dev)), net(torch.from_numpy(g["style"]).to(dev))
+    y = net(cWCT().transfer(zc, zs, g["cmask"], g["smask"]), forward=False)
+    assert maxdiff(y, g["stylized"]) <= PIXEL_TOL
+    assert maxdiff(y, g["stylized"]) <= 1e-4
+
+
+def test_full_size_properties_1080p(dev):
+    """BASELINE cfg4 size, size-independent properties: round trip at fp32 level; the cWCT output has the
+    style's mean and covariance; identity transfer (style == content) returns the content."""
+    from vstnet_b200 import cWCT
+    net = build_net("photo", 0, 7).to(dev)
+    x = torch.rand(1, 3, 1080, 1920, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    s = torch.rand(1, 3, 1080, 1920, device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+    z = net(x)
+    assert float((net.inverse(z) - x).abs().max()) <= 1e-6
+    zs = net(s)
+    zcs = cWCT().transfer(z, zs)
+    a, b = zcs[0].reshape(32, -1).double(), zs[0].reshape(32, -1).double()
+    assert float((a.mean(1) - b.mean(1)).abs().max()) <= 1e-5
+    assert float((torch.cov(a) - torch.cov(b)).abs().max()) <= 1e-4 * float(torch.cov(b).abs().max())
+    assert float((cWCT().transfer(z, z) - z).abs().max()) <= 1e-4
+    assert float((cWCT().interpolation(z, [zs], [1.0], 1.0) - z).abs().max()) <= 1e-5   # alpha_c = 1 keeps content
+
+
+def test_frame_conversion(dev):
+    import ctypes
+    from vstnet_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (20, 24, 3), generator=g, dtype=torch.uint8).to(dev)
+    f = torch.empty(3, 20, 24, device=dev)
+    _lib.check(lib.vst_frame_u8_to_f32(u8.data_ptr(), f.data_ptr(), 20, 24, 0, None), "u8_to_f32")
+    torch.cuda.synchronize()
+    assert torch.equal(f.cpu(), u8.cpu().permute(2, 0, 1).float() / 255)
+    y = (torch.rand(3, 20, 24, generator=g) * 1.4 - 0.2).to(dev)
+    o = torch.empty(20, 24, 3, dtype=torch.uint8, device=dev)
+    _lib.check(lib.vst_frame_f32_to_u8(y.data_ptr(), o.data_ptr(), 20, 24, 1, None), "f32_to_u8")
+    torch.cuda.synchronize()
+    ref = y.cpu().mul(255).clamp(0, 255).byte().permute(1, 2, 0).flip(-1)
+    assert torch.equal(o.cpu(), ref)

@@ -1,0 +1,166 @@
+"""Drop-in replacement for the reference's ``models/cWCT.py`` on B200.
+
+Same constructor and methods: ``cWCT(eps=2e-5, use_double=False)``,
+``transfer(content_feat, style_feat, cmask=None, smask=None)``,
+``interpolation(content_feat, styl_feat_list, alpha_s_list, alpha_c=0.0)``
+(ref: cWCT.py:9-262).  All arithmetic runs on the device in three hand-written kernels behind
+the C ABI (stats -> factor -> apply, see csrc/cwct.cu); there is no host round trip, no
+``np.where`` / index upload per label, and no CPU fallback.
+
+Deliberate differences from the fork, both documented in DESIGN.md:
+  * ``transfer`` without masks works (the fork's 3-D ``whitening`` raises); it
+    returns the intended upstream result, equal to ``interpolation(c, [s], [1.0], 0.0)``.
+  * masks may also be uint8 CUDA tensors (no upload); numpy uint8 ``[B,H,W]`` is accepted as in
+    the reference and must be at latent resolution (cWCT.py:72-73 uses them as-is).
+As in the reference, the masked path writes its result into ``content_feat`` in place
+(cWCT.py:103) and returns it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _check_feat(x, what):
+    if not isinstance(x, torch.Tensor) or x.dim() != 4:
+        raise ValueError("%s must be a 4-D tensor [B,N,H,W]" % what)
+    if not x.is_cuda:
+        raise RuntimeError("vstnet_b200.cWCT runs on CUDA (sm_100a) only; %s is on %s — there is no CPU fallback"
+                           % (what, x.device))
+    if x.dtype != torch.float32:
+        raise ValueError("%s must be float32 (got %s)" % (what, x.dtype))
+
+
+class cWCT(nn.Module):
+    """Cholesky decomposition based WCT (ref: cWCT.py:9-16)."""
+
+    def __init__(self, eps=2e-5, use_double=False):
+        super().__init__()
+        self.eps = eps
+        self.use_double = use_double
+        self._lib = _lib.load()
+        self.last_status = None     # int32 [L] device tensor of the last call: #jitter retries per label
+
+    # ------------------------------------------------------------------ low-level steps
+    def _stats(self, feat2d, C_, n, labels, L, stream):
+        buf = torch.empty(int(self._lib.vst_cwct_stats_bytes(C_, L)), dtype=torch.uint8, device=feat2d.device)
+        _lib.check(self._lib.vst_cwct_stats(feat2d.data_ptr(), C_, n, labels.data_ptr() if labels is not None else None,
+                                            L, buf.data_ptr(), stream), "vst_cwct_stats")
+        return buf
+
+    def _factor(self, cstats, sstats_list, alpha_s, alpha_c, C_, L, masked, device, stream):
+        T = torch.empty(L, C_, C_, dtype=torch.float32, device=device)
+        mu = torch.empty(L, C_, dtype=torch.float32, device=device)
+        beta = torch.empty(L, C_, dtype=torch.float32, device=device)
+        valid = torch.empty(L, dtype=torch.int32, device=device)
+        status = torch.empty(L, dtype=torch.int32, device=device)
+        K = len(sstats_list)
+        ptrs = (C.c_void_p * K)(*[s.data_ptr() for s in sstats_list])
+        alphas = (C.c_float * K)(*[float(a) for a in alpha_s])
+        _lib.check(self._lib.vst_cwct_factor(cstats.data_ptr(), ptrs, alphas, K, float(alpha_c), float(self.eps), C_, L,
+                                             int(masked), int(bool(self.use_double)), T.data_ptr(), mu.data_ptr(),
+                                             beta.data_ptr(), valid.data_ptr(), status.data_ptr(), stream),
+                   "vst_cwct_factor")
+        self.last_status = status
+        return T, mu, beta, valid
+
+    def _apply(self, feat2d, out2d, C_, n, labels, L, T, mu, beta, valid, stream):
+        _lib.check(self._lib.vst_cwct_apply(feat2d.data_ptr(), out2d.data_ptr(), C_, n,
+                                            labels.data_ptr() if labels is not None else None, L, T.data_ptr(),
+                                            mu.data_ptr(), beta.data_ptr(), valid.data_ptr(), stream), "vst_cwct_apply")
+
+    @staticmethod
+    def _mask_to_device(mask, n, device, what):
+        """One sample's label map -> flat uint8 device tensor of n labels (+ its max label)."""
+        if isinstance(mask, torch.Tensor):
+            if mask.dtype != torch.uint8:
+                raise ValueError("%s must be uint8" % what)
+            m = mask.reshape(-1).to(device).contiguous()
+            mx = int(m.max().item())
+        else:
+            a = np.ascontiguousarray(np.asarray(mask))
+            if a.dtype != np.uint8:
+                raise ValueError("%s must be uint8 (got %s)" % (what, a.dtype))
+            mx = int(a.max())
+            m = torch.from_numpy(a.reshape(-1)).to(device, non_blocking=False)
+        if m.numel() != n:
+            raise ValueError("%s has %d labels but the feature map has %d positions; masks must be at latent "
+                             "resolution (ref: cWCT.py:72-73)" % (what, m.numel(), n))
+        return m, mx
+
+    # ------------------------------------------------------------------ reference API
+    def transfer(self, content_feat, style_feat, cmask=None, smask=None):
+        """ref: cWCT.py:18-22."""
+        if cmask is None or smask is None:
+            return self._transfer(content_feat, style_feat)
+        return self._transfer_seg(content_feat, style_feat, cmask, smask)
+
+    @torch.no_grad()
+    def _transfer(self, content_feat, style_feat):
+        """Unmasked whitening + colouring (ref: cWCT.py:24-47, intended semantics)."""
+        return self.interpolation(content_feat, [style_feat], [1.0], 0.0)
+
+    @torch.no_grad()
+    def interpolation(self, content_feat, styl_feat_list, alpha_s_list, alpha_c=0.0):
+        """ref: cWCT.py:206-262."""
+        assert len(styl_feat_list) == len(alpha_s_list)
+        _check_feat(content_feat, "content_feat")
+        B, N, cH, cW = content_feat.shape
+        if len(styl_feat_list) < 1 or len(styl_feat_list) > _lib.MAX_STYLES:
+            raise ValueError("need 1..%d style features" % _lib.MAX_STYLES)
+        for s in styl_feat_list:
+            _check_feat(s, "style_feat")
+            assert s.shape[0] == B and s.shape[1] == N
+        if N > 128:
+            raise ValueError("vstnet_b200.cWCT supports at most 128 feature channels (got %d)" % N)
+        dev = content_feat.device
+        content = content_feat.contiguous()
+        styles = [s.contiguous() for s in styl_feat_list]
+        out = torch.empty_like(content)
+        n = cH * cW
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for i in range(B):
+                cst = self._stats(content[i], N, n, None, 1, st)
+                sst = [self._stats(s[i], N, s.shape[2] * s.shape[3], None, 1, st) for s in styles]
+                T, mu, beta, valid = self._factor(cst, sst, alpha_s_list, alpha_c, N, 1, False, dev, st)
+                self._apply(content[i], out[i], N, n, None, 1, T, mu, beta, valid, st)
+        return out
+
+    @torch.no_grad()
+    def _transfer_seg(self, content_feat, style_feat, cmask, smask):
+        """Per-label masked transfer (ref: cWCT.py:49-109).  Mutates and returns content_feat."""
+        _check_feat(content_feat, "content_feat")
+        _check_feat(style_feat, "style_feat")
+        B, N, cH, cW = content_feat.shape
+        _, _, sH, sW = style_feat.shape
+        if N > 128:
+            raise ValueError("vstnet_b200.cWCT supports at most 128 feature channels (got %d)" % N)
+        if not content_feat.is_contiguous():
+            raise ValueError("masked transfer writes into content_feat in place (ref: cWCT.py:103); it must be "
+                             "contiguous")
+        if len(cmask) != B or len(smask) != B:
+            raise ValueError("masks must have a leading batch dimension of %d" % B)
+        dev = content_feat.device
+        style = style_feat.contiguous()
+        nc, ns = cH * cW, sH * sW
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for i in range(B):
+                cm, cmax = self._mask_to_device(cmask[i], nc, dev, "cmask")
+                sm, _ = self._mask_to_device(smask[i], ns, dev, "smask")
+                # the reference sizes its validity table max(content label)+1 (cWCT.py:173-175);
+                # label 255 overflows its uint8 arithmetic there and raises IndexError.
+                if cmax >= 255:
+                    raise IndexError("content label 255 is not supported (ref: cWCT.py:173 overflows uint8)")
+                L = cmax + 1
+                cst = self._stats(content_feat[i], N, nc, cm, L, st)
+                sst = self._stats(style[i], N, ns, sm, L, st)
+                T, mu, beta, valid = self._factor(cst, [sst], [1.0], 0.0, N, L, True, dev, st)
+                self._apply(content_feat[i], content_feat[i], N, nc, cm, L, T, mu, beta, valid, st)
+        return content_feat

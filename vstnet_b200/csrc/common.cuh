@@ -1,0 +1,51 @@
+// common.cuh — shared helpers for libvstb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/vstb200.h"
+
+namespace vst {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// returns non-zero (and records the message) if the last launch failed to enqueue
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return 1;
+    }
+    count_launch();
+    return 0;
+}
+
+#define VST_CUDA_OK(expr)                                                            \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            vst::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 1;                                                                \
+        }                                                                            \
+    } while (0)
+
+#define VST_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            vst::set_error(__VA_ARGS__);  \
+            return 2;                     \
+        }                                 \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int num_sms();
+
+}  // namespace vst

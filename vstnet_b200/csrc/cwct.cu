@@ -1,0 +1,633 @@
+// cwct.cu — Cholesky whitening / colouring transform on the device, with no host round trips.
+//
+// Replaces models/cWCT.py: whitening :134-149, coloring :152-164, cholesky_dec :111-132,
+// _transfer :24-47, _transfer_seg :49-109 (+ compute_label_info :166-189, get_index :199-204),
+// interpolation :206-262.   Closed form, per label l:
+//     out = T_l (x - mu_c,l) + beta_l
+//     T_l    = (1-a_c) (sum_k a_k Ls_k) Lc^-1 + a_c I
+//     beta_l = (1-a_c) sum_k a_k mu_s,k + a_c mu_c
+//
+// Three kernels: (1) stats  — per-label count / sum / Gram in one pass over [C, n] features,
+// fp32 products, fp64 cross-tile accumulation, pivot-shifted to avoid cancellation;
+// (2) factor — one CTA per label: covariance, Cholesky with the cumulative eps*I retry,
+// triangular solve, all in fp64 shared memory; (3) apply — label-indexed C x C transform.
+#include "kernels.cuh"
+
+namespace vst {
+
+// ------------------------------------------------------------------------------------------
+// stats block layout (doubles unless noted):  count[L] | sum[L*C] | gram[L*C*C] | pivot[C] (float)
+// ------------------------------------------------------------------------------------------
+struct StatsView {
+    double* count;
+    double* sum;
+    double* gram;
+    float* pivot;
+};
+__host__ __device__ inline size_t stats_doubles(int C, int L) { return (size_t)L * (1 + C + (size_t)C * C); }
+__host__ __device__ inline StatsView stats_view(void* p, int C, int L) {
+    StatsView v;
+    v.count = (double*)p;
+    v.sum = v.count + L;
+    v.gram = v.sum + (size_t)L * C;
+    v.pivot = (float*)(v.gram + (size_t)L * C * C);
+    return v;
+}
+
+// pivot[c] = mean of up to 4096 evenly spaced samples of channel c
+__global__ void pivot_kernel(const float* __restrict__ feat, long long n, float* __restrict__ pivot) {
+    const int c = blockIdx.x;
+    const long long S = n < 4096 ? n : 4096;
+    float s = 0.f;
+    for (long long k = threadIdx.x; k < S; k += blockDim.x) s += __ldg(feat + (size_t)c * n + (k * n) / S);
+    __shared__ float red[32];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) pivot[c] = s / (float)S;
+    }
+}
+
+// ---- C <= 32: every warp owns a private 32x32 Gram in registers (lane: 4 rows x 8 cols) and
+// streams its own contiguous pixel range through a private smem sub-tile.
+template <bool MASKED>
+__global__ void __launch_bounds__(256) gram32_kernel(const float* __restrict__ feat, int C, long long n,
+                                                     const uint8_t* __restrict__ labels, int L, StatsView sv,
+                                                     long long chunk) {
+    __shared__ __align__(16) float tile[8][8][33][4];
+    __shared__ float piv[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 32) piv[threadIdx.x] = threadIdx.x < C ? sv.pivot[threadIdx.x] : 0.f;
+    __syncthreads();
+    const long long start = ((long long)blockIdx.x * 8 + warp) * chunk;
+    const long long end = start + chunk < n ? start + chunk : n;
+    const int gi = lane >> 2, gj = (lane & 3) * 2;   // row group, first col group
+
+    float acc[4][8];
+    float sacc = 0.f;
+    int cnt = 0, cur = MASKED ? -1 : 0, since = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+
+    auto flush = [&](int l) {
+        if (l >= 0 && l < L && cnt > 0) {
+            double* g = sv.gram + (size_t)l * C * C;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    int i = gi * 4 + a, j = gj * 4 + b;
+                    if (i < C && j < C) atomicAdd(g + (size_t)i * C + j, (double)acc[a][b]);
+                }
+            if (lane < C) atomicAdd(sv.sum + (size_t)l * C + lane, (double)sacc);
+            if (lane == 0) atomicAdd(sv.count + l, (double)cnt);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+        sacc = 0.f; cnt = 0; since = 0;
+    };
+
+    for (long long base = start; base < end; base += 32) {
+        const long long p = base + lane;
+        const bool ok = p < end;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            float4 v;
+            v.x = (ok && 4 * g + 0 < C) ? __ldg(feat + (size_t)(4 * g + 0) * n + p) - piv[4 * g + 0] : 0.f;
+            v.y = (ok && 4 * g + 1 < C) ? __ldg(feat + (size_t)(4 * g + 1) * n + p) - piv[4 * g + 1] : 0.f;
+            v.z = (ok && 4 * g + 2 < C) ? __ldg(feat + (size_t)(4 * g + 2) * n + p) - piv[4 * g + 2] : 0.f;
+            v.w = (ok && 4 * g + 3 < C) ? __ldg(feat + (size_t)(4 * g + 3) * n + p) - piv[4 * g + 3] : 0.f;
+            *reinterpret_cast<float4*>(tile[warp][g][lane]) = v;
+        }
+        int lab = 0;
+        if (MASKED) lab = ok ? (int)labels[p] : -1;
+        __syncwarp();
+        const int npx = (int)(end - base < 32 ? end - base : 32);
+        for (int q = 0; q < npx; ++q) {
+            if (MASKED) {
+                int l = __shfl_sync(0xffffffffu, lab, q);
+                if (l != cur) { flush(cur); cur = l; }
+            }
+            const float4 a4 = *reinterpret_cast<const float4*>(tile[warp][gi][q]);
+            const float4 b0 = *reinterpret_cast<const float4*>(tile[warp][gj][q]);
+            const float4 b1 = *reinterpret_cast<const float4*>(tile[warp][gj + 1][q]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            sacc += tile[warp][lane >> 2][q][lane & 3];
+            ++cnt;
+        }
+        __syncwarp();
+        since += 32;
+        if (since >= 1024) flush(cur);   // bound the fp32 run length; the cross-run sum is fp64
+    }
+    flush(cur);
+}
+
+// ---- 32 < C <= 128: the CTA owns one 128x128 Gram (thread: 8 rows x 8 cols) and streams a
+// contiguous pixel range through a shared [group][pixel][4] tile.
+template <bool MASKED>
+__global__ void __launch_bounds__(256) gram128_kernel(const float* __restrict__ feat, int C, long long n,
+                                                      const uint8_t* __restrict__ labels, int L, StatsView sv,
+                                                      long long chunk) {
+    __shared__ __align__(16) float tile[32][33][4];
+    __shared__ float piv[128];
+    __shared__ int labs[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 128) piv[tid] = tid < C ? sv.pivot[tid] : 0.f;
+    __syncthreads();
+    const long long start = (long long)blockIdx.x * chunk;
+    const long long end = start + chunk < n ? start + chunk : n;
+    const int ti = tid >> 4, tj = tid & 15;   // rows 8ti..8ti+7 ; cols 4tj..4tj+3 and 64+4tj..64+4tj+3
+
+    float acc[8][8];
+    float sacc = 0.f;
+    int cnt = 0, cur = MASKED ? -1 : 0, since = 0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+
+    auto flush = [&](int l) {
+        if (l >= 0 && l < L && cnt > 0) {
+            double* g = sv.gram + (size_t)l * C * C;
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    int i = ti * 8 + a, j = (b < 4) ? tj * 4 + b : 64 + tj * 4 + (b - 4);
+                    if (i < C && j < C) atomicAdd(g + (size_t)i * C + j, (double)acc[a][b]);
+                }
+            if (tid < C) atomicAdd(sv.sum + (size_t)l * C + tid, (double)sacc);
+            if (tid == 0) atomicAdd(sv.count + l, (double)cnt);
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+        sacc = 0.f; cnt = 0; since = 0;
+    };
+
+    for (long long base = start; base < end; base += 32) {
+        const long long p = base + lane;
+        const bool ok = p < end;
+        __syncthreads();   // previous tile fully consumed
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+            const int g = warp * 4 + gg;
+            float4 v;
+            v.x = (ok && 4 * g + 0 < C) ? __ldg(feat + (size_t)(4 * g + 0) * n + p) - piv[4 * g + 0] : 0.f;
+            v.y = (ok && 4 * g + 1 < C) ? __ldg(feat + (size_t)(4 * g + 1) * n + p) - piv[4 * g + 1] : 0.f;
+            v.z = (ok && 4 * g + 2 < C) ? __ldg(feat + (size_t)(4 * g + 2) * n + p) - piv[4 * g + 2] : 0.f;
+            v.w = (ok && 4 * g + 3 < C) ? __ldg(feat + (size_t)(4 * g + 3) * n + p) - piv[4 * g + 3] : 0.f;
+            *reinterpret_cast<float4*>(tile[g][lane]) = v;
+        }
+        if (MASKED && warp == 0) labs[lane] = ok ? (int)labels[p] : -1;
+        __syncthreads();
+        const int npx = (int)(end - base < 32 ? end - base : 32);
+        for (int q = 0; q < npx; ++q) {
+            if (MASKED) {
+                int l = labs[q];
+                if (l != cur) { flush(cur); cur = l; }
+            }
+            const float4 a0 = *reinterpret_cast<const float4*>(tile[2 * ti][q]);
+            const float4 a1 = *reinterpret_cast<const float4*>(tile[2 * ti + 1][q]);
+            const float4 b0 = *reinterpret_cast<const float4*>(tile[tj][q]);
+            const float4 b1 = *reinterpret_cast<const float4*>(tile[tj + 16][q]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+            if (tid < 128) sacc += tile[tid >> 2][q][tid & 3];
+            ++cnt;
+        }
+        since += 32;
+        if (since >= 1024) flush(cur);
+    }
+    flush(cur);
+}
+
+// ------------------------------------------------------------------------------------------
+// factor: one CTA per label
+// ------------------------------------------------------------------------------------------
+struct FactorArgs {
+    const void* cstats;
+    const void* sstats[VST_MAX_STYLES];
+    float alpha_s[VST_MAX_STYLES];
+    int n_styles;
+    float alpha_c, eps;
+    int C, L, masked, use_double;
+    float *T, *mu, *beta;
+    int *valid, *status;
+};
+
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
+
+// covariance (+ jitter) of one label from a stats block into packed-lower A; returns nothing
+__device__ void build_cov(double* A, const StatsView& sv, int l, int C, double n, double jitter, bool round32) {
+    const double* G = sv.gram + (size_t)l * C * C;
+    const double* s = sv.sum + (size_t)l * C;
+    for (int e = threadIdx.x; e < C * (C + 1) / 2; e += blockDim.x) {
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (tri(i + 1, 0) <= e) ++i;
+        while (tri(i, 0) > e) --i;
+        int j = e - tri(i, 0);
+        // average the two triangles: the Gram is accumulated unsymmetrised
+        double g = 0.5 * (G[(size_t)i * C + j] + G[(size_t)j * C + i]);
+        double c = (g - s[i] * s[j] / n) / (n - 1.0);
+        if (round32) c = (double)(float)c;          // the reference's covariance is an fp32 matrix
+        if (i == j) c += jitter;
+        A[e] = c;
+    }
+}
+
+// in-place packed-lower Cholesky; returns false (uniformly) when a pivot is not safely positive
+__device__ bool cholesky_packed(double* A, int C, int* flag) {
+    for (int k = 0; k < C; ++k) {
+        if (threadIdx.x == 0) {
+            double d = A[tri(k, k)];
+            // LAPACK potrf fails on d <= 0 or NaN; fp32 LAPACK additionally cannot tell a pivot
+            // below its rounding noise from zero, so treat those as failures too.
+            if (!(d > 0.0)) *flag = 1;
+            else A[tri(k, k)] = sqrt(d);
+        }
+        __syncthreads();
+        if (*flag) return false;
+        const double inv = 1.0 / A[tri(k, k)];
+        __syncthreads();
+        for (int i = k + 1 + threadIdx.x; i < C; i += blockDim.x) A[tri(i, k)] *= inv;
+        __syncthreads();
+        const int m = C - k - 1;   // trailing size
+        for (int e = threadIdx.x; e < m * (m + 1) / 2; e += blockDim.x) {
+            int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (tri(a + 1, 0) <= e) ++a;
+            while (tri(a, 0) > e) --a;
+            int b = e - tri(a, 0);
+            int i = k + 1 + a, j = k + 1 + b;
+            A[tri(i, j)] -= A[tri(i, k)] * A[tri(j, k)];
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
+// cov -> L with the reference's retry rule (cWCT.py:115-128): first try as is, then add eps, then
+// 2 eps more, ... (cumulative eps*k(k+1)/2).  Returns #retries, or -1 if it never succeeded.
+__device__ int chol_retry(double* A, const StatsView& sv, int l, int C, double n, double eps, bool round32, int* flag) {
+    for (int k = 0; k <= 64; ++k) {
+        __syncthreads();
+        if (threadIdx.x == 0) *flag = 0;
+        build_cov(A, sv, l, C, n, eps * (double)(k * (k + 1) / 2), round32);
+        __syncthreads();
+        // rank-deficient labels (n <= C): the exact pivot is 0 and the computed one is rounding
+        // noise of either sign; the reference (fp32 LAPACK on an fp32 matrix) sees noise ~1e-8 *
+        // |diag|.  Make the outcome deterministic: a pivot below that noise floor is a failure.
+        if (cholesky_packed(A, C, flag)) {
+            __shared__ int bad;
+            if (threadIdx.x == 0) bad = 0;
+            __syncthreads();
+            // relative check of the factor's diagonal against the matrix diagonal
+            const StatsView& s2 = sv;
+            for (int i = threadIdx.x; i < C; i += blockDim.x) {
+                double g = s2.gram[(size_t)l * C * C + (size_t)i * C + i];
+                double si = s2.sum[(size_t)l * C + i];
+                double cii = (g - si * si / n) / (n - 1.0) + eps * (double)(k * (k + 1) / 2);
+                double lii = A[tri(i, i)];
+                if (!(lii * lii > 1e-7 * cii)) bad = 1;
+            }
+            __syncthreads();
+            if (!bad) return k;
+        }
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) factor_kernel(FactorArgs fa) {
+    extern __shared__ __align__(16) double sm[];
+    const int C = fa.C, L = fa.L, l = blockIdx.x;
+    const int TRI = C * (C + 1) / 2;
+    double* Lc = sm;             // packed lower
+    double* Ls = sm + TRI;       // packed lower (per style)
+    double* Mix = sm + 2 * TRI;  // packed lower: sum_k a_k Ls_k
+    double* mu_c = sm + 3 * TRI; // [C]
+    double* mu_m = mu_c + C;     // [C] mixed style mean
+    __shared__ int flag;
+    __shared__ int ok_s;
+
+    const StatsView cs = stats_view(const_cast<void*>(fa.cstats), C, L);
+    const double nc = cs.count[l];
+    float* T = fa.T + (size_t)l * C * C;
+
+    bool ok = nc >= 2.0;
+    for (int k = 0; k < fa.n_styles && ok; ++k) {
+        const double ns = stats_view(const_cast<void*>(fa.sstats[k]), C, L).count[l];
+        ok = ns >= 2.0;
+        if (fa.masked)   // cWCT.py:178
+            ok = ok && nc > 10.0 && ns > 10.0 && nc / ns < 100.0 && ns / nc < 100.0;
+    }
+    int retries = 0;
+    if (ok) {
+        int r = chol_retry(Lc, cs, l, C, nc, (double)fa.eps, !fa.use_double, &flag);
+        if (r < 0) ok = false; else retries += r;
+    }
+    for (int e = threadIdx.x; e < TRI; e += blockDim.x) Mix[e] = 0.0;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        mu_c[i] = ok ? (double)cs.pivot[i] + cs.sum[(size_t)l * C + i] / nc : 0.0;
+        mu_m[i] = 0.0;
+    }
+    __syncthreads();
+    for (int k = 0; k < fa.n_styles && ok; ++k) {
+        const StatsView ss = stats_view(const_cast<void*>(fa.sstats[k]), C, L);
+        const double ns = ss.count[l];
+        int r = chol_retry(Ls, ss, l, C, ns, (double)fa.eps, !fa.use_double, &flag);
+        if (r < 0) { ok = false; break; }
+        retries += r;
+        const double a = (double)fa.alpha_s[k];
+        for (int e = threadIdx.x; e < TRI; e += blockDim.x) Mix[e] += a * Ls[e];
+        for (int i = threadIdx.x; i < C; i += blockDim.x)
+            mu_m[i] += a * ((double)ss.pivot[i] + ss.sum[(size_t)l * C + i] / ns);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ok_s = ok ? 1 : 0;
+    __syncthreads();
+    ok = ok_s != 0;
+
+    const double ac = (double)fa.alpha_c;
+    if (ok) {
+        // row r of X = Mix Lc^-1 solves  X[r,:] Lc = Mix[r,:]   (back substitution, j = r..0)
+        for (int r = threadIdx.x; r < C; r += blockDim.x) {
+            // reuse Ls storage row r (length r+1) for the solution; Mix row r is the rhs
+            double* x = Ls + tri(r, 0);
+            for (int j = r; j >= 0; --j) {
+                double s = Mix[tri(r, j)];
+                for (int k = j + 1; k <= r; ++k) s -= x[k] * Lc[tri(k, j)];
+                x[j] = s / Lc[tri(j, j)];
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
+            int i = e / C, j = e - i * C;
+            double v = (j <= i) ? (1.0 - ac) * Ls[tri(i, j)] : 0.0;
+            if (i == j) v += ac;
+            T[e] = (float)v;
+        }
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            fa.mu[(size_t)l * C + i] = (float)mu_c[i];
+            fa.beta[(size_t)l * C + i] = (float)((1.0 - ac) * mu_m[i] + ac * mu_c[i]);
+        }
+    } else {
+        for (int e = threadIdx.x; e < C * C; e += blockDim.x) T[e] = (e / C == e % C) ? 1.f : 0.f;
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            fa.mu[(size_t)l * C + i] = 0.f;
+            fa.beta[(size_t)l * C + i] = 0.f;
+        }
+    }
+    if (threadIdx.x == 0) {
+        fa.valid[l] = ok ? 1 : 0;
+        fa.status[l] = ok ? retries : ((nc >= 2.0 && !fa.masked) ? -1 : 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// apply:  out[:,p] = T[l(p)] (x[:,p] - mu[l(p)]) + beta[l(p)]
+// thread tile = 8 output channels x 4 pixels; CTA tile = CP channels x PX pixels
+// ------------------------------------------------------------------------------------------
+template <int CP>
+struct ApplyCfg {
+    static constexpr int NCG = CP / 8;          // channel groups
+    static constexpr int NPG = 256 / NCG;       // pixel groups
+    static constexpr int PX = NPG * 4;          // pixels per tile
+    static constexpr size_t SMEM = (size_t)(CP * PX + CP * CP + 2 * CP) * sizeof(float) + PX * sizeof(int);
+};
+
+template <int CP>
+__global__ void __launch_bounds__(256) apply_kernel(const float* __restrict__ feat, float* __restrict__ out, int C,
+                                                    long long n, const uint8_t* __restrict__ labels, int L,
+                                                    const float* __restrict__ T, const float* __restrict__ mu,
+                                                    const float* __restrict__ beta, const int* __restrict__ valid,
+                                                    long long n_tiles) {
+    using Cfg = ApplyCfg<CP>;
+    constexpr int PX = Cfg::PX, NPG = Cfg::NPG;
+    extern __shared__ __align__(16) float smf[];
+    float* xs = smf;                   // [CP][PX]
+    float* Tt = xs + CP * PX;          // [k][c] (transposed)
+    float* mu_s = Tt + CP * CP;        // [CP]
+    float* be_s = mu_s + CP;           // [CP]
+    int* lab_s = (int*)(be_s + CP);    // [PX]
+    const int tid = threadIdx.x;
+    const int pg = tid % NPG, cg = tid / NPG;
+    int cached = -1;
+
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long p0 = t * PX;
+        const int npx = (int)(n - p0 < PX ? n - p0 : PX);
+        __syncthreads();   // previous tile's smem fully consumed
+        // ---- labels of this tile; is it uniform?
+        int uni = 0;
+        if (labels) {
+            int mine_ok = 1;
+            const int l0 = (int)labels[p0];
+            for (int i = tid; i < npx; i += 256) {
+                int l = (int)labels[p0 + i];
+                lab_s[i] = l;
+                mine_ok &= (l == l0);
+            }
+            uni = __syncthreads_and(mine_ok) ? l0 : -1;
+        }
+        // ---- stage x (raw)
+        for (int i = tid; i < CP * PX; i += 256) {
+            int k = i / PX, px = i - k * PX;
+            xs[i] = (k < C && px < npx) ? __ldg(feat + (size_t)k * n + p0 + px) : 0.f;
+        }
+        if (uni >= 0 && uni != cached) {
+            const int l = uni < L ? uni : 0;
+            const bool v = uni < L && valid[l];
+            for (int i = tid; i < CP * CP; i += 256) {
+                int k = i / CP, c = i - k * CP;     // Tt[k][c] = T[c][k]
+                float tv = (c == k) ? 1.f : 0.f;
+                if (v && c < C && k < C) tv = __ldg(T + ((size_t)l * C + c) * C + k);
+                else if (c >= C || k >= C) tv = 0.f;
+                Tt[i] = tv;
+            }
+            for (int i = tid; i < CP; i += 256) {
+                mu_s[i] = (v && i < C) ? mu[(size_t)l * C + i] : 0.f;
+                be_s[i] = (v && i < C) ? beta[(size_t)l * C + i] : 0.f;
+            }
+            cached = uni;
+        }
+        __syncthreads();
+
+        if (uni >= 0) {
+            const bool v = uni < L && valid[uni < L ? uni : 0];
+            if (!v) {   // invalid label: content features pass through untouched (cWCT.py:80-84)
+                if (out != feat)
+                    for (int i = tid; i < CP * PX; i += 256) {
+                        int k = i / PX, px = i - k * PX;
+                        if (k < C && px < npx) out[(size_t)k * n + p0 + px] = xs[i];
+                    }
+                continue;
+            }
+            float acc[8][4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < CP; ++k) {
+                const float4 x4 = *reinterpret_cast<const float4*>(xs + k * PX + pg * 4);
+                const float4 t0 = *reinterpret_cast<const float4*>(Tt + k * CP + cg * 8);
+                const float4 t1 = *reinterpret_cast<const float4*>(Tt + k * CP + cg * 8 + 4);
+                const float m = mu_s[k];
+                const float xv[4] = {x4.x - m, x4.y - m, x4.z - m, x4.w - m};
+                const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(tv[a], xv[b], acc[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int c = cg * 8 + a;
+                if (c >= C) continue;
+                const float bt = be_s[c];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int px = pg * 4 + b;
+                    if (px < npx) out[(size_t)c * n + p0 + px] = acc[a][b] + bt;
+                }
+            }
+        } else {
+            // ---- mixed-label tile: per-pixel transform straight from global T (rare: region borders)
+            for (int i = tid; i < npx * (CP / 8); i += 256) {
+                const int px = i % npx, c0 = (i / npx) * 8;
+                const int l = lab_s[px];
+                const bool v = l < L && valid[l < L ? l : 0];
+                float r[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) r[a] = 0.f;
+                if (v) {
+                    for (int k = 0; k < C; ++k) {
+                        const float xv = xs[k * PX + px] - __ldg(mu + (size_t)l * C + k);
+#pragma unroll
+                        for (int a = 0; a < 8; ++a)
+                            if (c0 + a < C) r[a] = fmaf(__ldg(T + ((size_t)l * C + c0 + a) * C + k), xv, r[a]);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int c = c0 + a;
+                    if (c >= C) continue;
+                    out[(size_t)c * n + p0 + px] = v ? r[a] + __ldg(beta + (size_t)l * C + c) : xs[c * PX + px];
+                }
+            }
+        }
+    }
+}
+
+template <int CP>
+static int launch_apply(const float* feat, float* out, int C, long long n, const uint8_t* labels, int L, const float* T,
+                        const float* mu, const float* beta, const int* valid, cudaStream_t st) {
+    using Cfg = ApplyCfg<CP>;
+    static bool attr_set = false;
+    auto kern = apply_kernel<CP>;
+    if (!attr_set) {
+        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    long long tiles = (n + Cfg::PX - 1) / Cfg::PX;
+    int grid = (int)std::min<long long>(tiles, (long long)num_sms() * (CP == 32 ? 4 : 2));
+    kern<<<grid, 256, Cfg::SMEM, st>>>(feat, out, C, n, labels, L, T, mu, beta, valid, tiles);
+    return check_launch("cwct_apply");
+}
+
+}  // namespace vst
+
+using namespace vst;
+
+extern "C" size_t vst_cwct_stats_bytes(int C, int n_labels) {
+    if (C < 1 || n_labels < 1) return 0;
+    return align_up(stats_doubles(C, n_labels) * sizeof(double) + (size_t)C * sizeof(float), 16);
+}
+
+extern "C" int vst_cwct_stats(const float* feat, int C, long long n, const uint8_t* labels, int n_labels, void* stats,
+                              void* stream) {
+    VST_REQUIRE(feat && stats, "vst_cwct_stats: null argument");
+    VST_REQUIRE(C >= 1 && C <= 128, "cWCT supports 1 <= C <= 128 channels (got %d)", C);
+    VST_REQUIRE(n >= 1, "vst_cwct_stats: empty feature map");
+    VST_REQUIRE(n_labels >= 1 && n_labels <= VST_MAX_LABELS, "n_labels %d out of range", n_labels);
+    VST_REQUIRE(labels || n_labels == 1, "unmasked stats need n_labels == 1");
+    VST_REQUIRE(((uintptr_t)stats & 7) == 0, "stats buffer must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    StatsView sv = stats_view(stats, C, n_labels);
+    VST_CUDA_OK(cudaMemsetAsync(stats, 0, stats_doubles(C, n_labels) * sizeof(double), st));
+    count_launch();
+    pivot_kernel<<<C, 256, 0, st>>>(feat, n, sv.pivot);
+    if (check_launch("cwct_pivot")) return 1;
+    const int sms = num_sms();
+    if (C <= 32) {
+        int grid = sms * 3;
+        long long warps = (long long)grid * 8;
+        long long chunk = ((n + warps - 1) / warps + 31) / 32 * 32;
+        grid = (int)((n + chunk * 8 - 1) / (chunk * 8));
+        if (labels) gram32_kernel<true><<<grid, 256, 0, st>>>(feat, C, n, labels, n_labels, sv, chunk);
+        else gram32_kernel<false><<<grid, 256, 0, st>>>(feat, C, n, labels, n_labels, sv, chunk);
+    } else {
+        int grid = sms * 3;
+        long long chunk = ((n + grid - 1) / grid + 31) / 32 * 32;
+        grid = (int)((n + chunk - 1) / chunk);
+        if (labels) gram128_kernel<true><<<grid, 256, 0, st>>>(feat, C, n, labels, n_labels, sv, chunk);
+        else gram128_kernel<false><<<grid, 256, 0, st>>>(feat, C, n, labels, n_labels, sv, chunk);
+    }
+    return check_launch("cwct_gram");
+}
+
+extern "C" int vst_cwct_factor(const void* content_stats, const void* const* style_stats, const float* alpha_s,
+                               int n_styles, float alpha_c, float eps, int C, int n_labels, int masked, int use_double,
+                               float* T, float* mu, float* beta, int* valid, int* status, void* stream) {
+    VST_REQUIRE(content_stats && style_stats && alpha_s && T && mu && beta && valid && status,
+                "vst_cwct_factor: null argument");
+    VST_REQUIRE(C >= 1 && C <= 128, "cWCT supports 1 <= C <= 128 channels (got %d)", C);
+    VST_REQUIRE(n_styles >= 1 && n_styles <= VST_MAX_STYLES, "n_styles %d out of range", n_styles);
+    VST_REQUIRE(n_labels >= 1 && n_labels <= VST_MAX_LABELS, "n_labels %d out of range", n_labels);
+    VST_REQUIRE(!masked || n_styles == 1, "masked transfer takes exactly one style (cWCT.py:49)");
+    FactorArgs fa;
+    fa.cstats = content_stats;
+    for (int k = 0; k < n_styles; ++k) {
+        VST_REQUIRE(style_stats[k], "style_stats[%d] is null", k);
+        fa.sstats[k] = style_stats[k];
+        fa.alpha_s[k] = alpha_s[k];
+    }
+    fa.n_styles = n_styles; fa.alpha_c = alpha_c; fa.eps = eps;
+    fa.C = C; fa.L = n_labels; fa.masked = masked; fa.use_double = use_double;
+    fa.T = T; fa.mu = mu; fa.beta = beta; fa.valid = valid; fa.status = status;
+    const size_t smem = ((size_t)3 * (C * (C + 1) / 2) + 2 * C) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VST_CUDA_OK(cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (128 * 129 / 2) * 8 + 2 * 128 * 8));
+        attr_set = true;
+    }
+    factor_kernel<<<n_labels, 256, smem, (cudaStream_t)stream>>>(fa);
+    return check_launch("cwct_factor");
+}
+
+extern "C" int vst_cwct_apply(const float* feat, float* out, int C, long long n, const uint8_t* labels, int n_labels,
+                              const float* T, const float* mu, const float* beta, const int* valid, void* stream) {
+    VST_REQUIRE(feat && out && T && mu && beta && valid, "vst_cwct_apply: null argument");
+    VST_REQUIRE(C >= 1 && C <= 128, "cWCT supports 1 <= C <= 128 channels (got %d)", C);
+    VST_REQUIRE(n >= 1, "vst_cwct_apply: empty feature map");
+    VST_REQUIRE(n_labels >= 1 && n_labels <= VST_MAX_LABELS, "n_labels %d out of range", n_labels);
+    if (C <= 32) return launch_apply<32>(feat, out, C, n, labels, n_labels, T, mu, beta, valid, (cudaStream_t)stream);
+    return launch_apply<128>(feat, out, C, n, labels, n_labels, T, mu, beta, valid, (cudaStream_t)stream);
+}

@@ -1,0 +1,295 @@
+// revnet.cu — host-side plan and dispatch of the reversible network (encode / decode).
+//
+// Replaces models/RevResNet.py:166-239 (RevResNet), :68-116 (residual_block), :119-163
+// (channel_reduction).  The plan holds no device memory; every buffer is carved out of the
+// caller's workspace.  State convention: the two half-states (s0,s1) live in two of three
+// rotating planar buffers; an additive-coupling block updates one half IN PLACE
+//     forward : s0 <- s0 + F(s1) ; swap       (RevResNet.py:96-104)
+//     inverse : s1 <- s1 - F(s0) ; swap       (RevResNet.py:106-116)
+// so split()/merge() (RevResNet.py:8-16) are pointer bookkeeping, not copies.
+#include <vector>
+#include <new>
+#include "kernels.cuh"
+
+namespace vst {
+
+struct ConvDesc {
+    int Cin, Cout, CoutPad, stride;
+    size_t raw_w, raw_b;  // float offsets into the flat raw parameter buffer
+    size_t pk_w, pk_b;    // float offsets into the packed buffer
+};
+struct BlockDesc {
+    int channel, stride;
+    ConvDesc conv[3];
+};
+
+}  // namespace vst
+
+struct vst_revnet {
+    vst_revnet_config cfg;
+    std::vector<vst::BlockDesc> stack, cr;
+    size_t raw_floats = 0, packed_floats = 0;
+    int precision = VST_CONV_FP32;
+    int c0 = 0;          // half-state channels at full resolution
+    int c_last = 0;      // half-state channels after the stack
+    int cr_channel = 0;  // channel_reduction block width (hidden_dim * 4^sp_steps)
+    int down = 1;        // prod(strides)
+};
+
+namespace vst {
+
+static void add_block(vst_revnet* n, std::vector<BlockDesc>& dst, int channel, int stride) {
+    BlockDesc b;
+    b.channel = channel;
+    b.stride = stride;
+    const int mid = channel / n->cfg.mult;
+    const int in_ch = (stride == 1) ? channel : channel / 4;   // RevResNet.py:74-77
+    const int cin[3] = {in_ch, mid, mid}, cout[3] = {mid, mid, channel}, st[3] = {stride, 1, 1};
+    for (int k = 0; k < 3; ++k) {
+        ConvDesc& c = b.conv[k];
+        c.Cin = cin[k]; c.Cout = cout[k]; c.stride = st[k];
+        c.CoutPad = conv_cout_pad(c.Cout);
+        c.raw_w = n->raw_floats; n->raw_floats += (size_t)c.Cout * c.Cin * 9;
+        c.raw_b = n->raw_floats; n->raw_floats += (size_t)c.Cout;
+        c.pk_w = n->packed_floats; n->packed_floats += (size_t)c.Cin * 9 * c.CoutPad;
+        c.pk_b = n->packed_floats; n->packed_floats += (size_t)c.CoutPad;
+    }
+    dst.push_back(b);
+}
+
+struct Shape { int c, h, w; };
+
+struct Workspace {
+    float* P[3];
+    float* T1;
+    float* T2;
+};
+
+static size_t half_state_floats(const vst_revnet* n, int H, int W) {
+    size_t a = (size_t)n->c0 * H * W;
+    size_t b = (size_t)n->cr_channel * (H / n->down) * (W / n->down);
+    return align_up(std::max(a, b), 64);
+}
+static size_t temp_floats(const vst_revnet* n, int H, int W) {
+    // largest bottleneck tensor: (channel/mult) x h x w over all blocks
+    size_t m = 0;
+    int h = H, w = W;
+    for (const BlockDesc& b : n->stack) {
+        if (b.stride == 2) { h /= 2; w /= 2; }
+        m = std::max(m, (size_t)(b.channel / n->cfg.mult) * h * w);
+    }
+    for (const BlockDesc& b : n->cr) m = std::max(m, (size_t)(b.channel / n->cfg.mult) * h * w);
+    return align_up(m, 64);
+}
+
+static int carve(const vst_revnet* n, int H, int W, void* ws, size_t ws_bytes, Workspace* out) {
+    size_t hs = half_state_floats(n, H, W), ts = temp_floats(n, H, W);
+    size_t need = (3 * hs + 2 * ts) * sizeof(float);
+    VST_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: have %zu bytes, need %zu", ws_bytes, need);
+    VST_REQUIRE(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
+    float* p = (float*)ws;
+    for (int i = 0; i < 3; ++i) { out->P[i] = p; p += hs; }
+    out->T1 = p; p += ts;
+    out->T2 = p;
+    return 0;
+}
+
+static ConvArgs conv_args(const ConvDesc& c, const float* packed, const float* in, int Hin, int Win, float* out,
+                          const float* res, int epi) {
+    ConvArgs a;
+    a.in = in; a.w = packed + c.pk_w; a.bias = packed + c.pk_b; a.res = res; a.out = out;
+    a.Cin = c.Cin; a.Cout = c.Cout; a.CoutPad = c.CoutPad;
+    a.Hin = Hin; a.Win = Win; a.Hout = Hin / c.stride; a.Wout = Win / c.stride;
+    a.epi = epi;
+    return a;
+}
+
+// F(x) = conv3(relu(conv2(relu(conv1(x)))))  with the coupling fused into conv3's epilogue
+static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, const float* x, int Hin, int Win,
+                 const Workspace& ws, const float* res, float* out, int epi, cudaStream_t st) {
+    const int Ho = Hin / b.stride, Wo = Win / b.stride;
+    (void)n;
+    if (launch_conv3x3_ffma(conv_args(b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU), b.stride, st)) return 1;
+    if (launch_conv3x3_ffma(conv_args(b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU), 1, st)) return 1;
+    if (launch_conv3x3_ffma(conv_args(b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi), 1, st)) return 1;
+    return 0;
+}
+
+static int forward_one(const vst_revnet* n, const float* packed, const float* x, float* z, int H, int W,
+                       const Workspace& ws, cudaStream_t st) {
+    float *s0 = ws.P[0], *s1 = ws.P[1], *spare = ws.P[2];
+    const size_t plane = (size_t)H * W;
+    // injective_pad + split (RevResNet.py:24-28, :8-12): s0 = [x, 0...], s1 = 0
+    VST_CUDA_OK(cudaMemcpyAsync(s0, x, (size_t)n->cfg.in_channel * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    VST_CUDA_OK(cudaMemsetAsync(s0 + (size_t)n->cfg.in_channel * plane, 0,
+                                (size_t)(n->c0 - n->cfg.in_channel) * plane * sizeof(float), st));
+    VST_CUDA_OK(cudaMemsetAsync(s1, 0, (size_t)n->c0 * plane * sizeof(float), st));
+    count_launch(3);
+
+    int c = n->c0, h = H, w = W;
+    for (const BlockDesc& b : n->stack) {
+        if (b.stride == 1) {
+            if (run_F(n, b, packed, s1, h, w, ws, s0, s0, EPI_ADD, st)) return 1;
+            std::swap(s0, s1);
+        } else {
+            // y1 = F(s1) + squeeze(s0) -> spare ; new x1 = squeeze(s1) -> old s0 buffer
+            if (run_F(n, b, packed, s1, h, w, ws, s0, spare, EPI_ADD_SQZ, st)) return 1;
+            if (launch_space_to_depth(s1, s0, c, h, w, st)) return 1;
+            float* old_s1 = s1;
+            s1 = spare; spare = old_s1;      // (s0, s1) = (squeeze(x2), y1)
+            c *= 4; h /= 2; w /= 2;
+        }
+    }
+    if (n->cr_channel > c) {   // channel_reduction's injective pad (RevResNet.py:133-134)
+        size_t pl = (size_t)h * w;
+        VST_CUDA_OK(cudaMemsetAsync(s0 + (size_t)c * pl, 0, (size_t)(n->cr_channel - c) * pl * sizeof(float), st));
+        VST_CUDA_OK(cudaMemsetAsync(s1 + (size_t)c * pl, 0, (size_t)(n->cr_channel - c) * pl * sizeof(float), st));
+        count_launch(2);
+    }
+    for (const BlockDesc& b : n->cr) {
+        if (run_F(n, b, packed, s1, h, w, ws, s0, s0, EPI_ADD, st)) return 1;
+        std::swap(s0, s1);
+    }
+    return launch_latent_spread(s0, s1, z, n->cr_channel, h, w, n->cfg.sp_steps, st);
+}
+
+static int inverse_one(const vst_revnet* n, const float* packed, const float* z, float* x, int H, int W,
+                       const Workspace& ws, cudaStream_t st) {
+    float *s0 = ws.P[0], *s1 = ws.P[1], *spare = ws.P[2];
+    int h = H / n->down, w = W / n->down;
+    if (launch_latent_gather(z, s0, s1, n->cr_channel, h, w, n->cfg.sp_steps, st)) return 1;
+    for (int i = (int)n->cr.size() - 1; i >= 0; --i) {
+        if (run_F(n, n->cr[i], packed, s0, h, w, ws, s1, s1, EPI_SUB, st)) return 1;
+        std::swap(s0, s1);
+    }
+    int c = n->c_last;   // channel_reduction's pad channels are dropped by simply ignoring them
+    for (int i = (int)n->stack.size() - 1; i >= 0; --i) {
+        const BlockDesc& b = n->stack[i];
+        if (b.stride == 1) {
+            if (run_F(n, b, packed, s0, h, w, ws, s1, s1, EPI_SUB, st)) return 1;
+            std::swap(s0, s1);
+        } else {
+            // x2 = unsqueeze(s0) -> spare ; x1 = unsqueeze(s1 - F(x2)) -> old s0 buffer
+            if (launch_depth_to_space(s0, spare, c / 4, h, w, st)) return 1;
+            if (run_F(n, b, packed, spare, 2 * h, 2 * w, ws, s1, s0, EPI_SUB_UNSQZ, st)) return 1;
+            float* old_s1 = s1;
+            s1 = spare; spare = old_s1;      // (s0, s1) = (x1, x2)
+            c /= 4; h *= 2; w *= 2;
+        }
+    }
+    // merge + injective_pad.inverse (RevResNet.py:30-31): keep the first in_channel planes of x1
+    VST_CUDA_OK(cudaMemcpyAsync(x, s0, (size_t)n->cfg.in_channel * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    count_launch(1);
+    return 0;
+}
+
+}  // namespace vst
+
+using namespace vst;
+
+extern "C" int vst_revnet_create(const vst_revnet_config* cfg, vst_revnet** out) {
+    VST_REQUIRE(cfg && out, "vst_revnet_create: null argument");
+    VST_REQUIRE(cfg->n_stages >= 1 && cfg->n_stages <= VST_MAX_STAGES, "n_stages %d out of range", cfg->n_stages);
+    VST_REQUIRE(cfg->mult >= 1 && cfg->sp_steps >= 0 && cfg->hidden_dim >= 1 && cfg->n_cr_blocks >= 0,
+                "bad mult/sp_steps/hidden_dim/n_cr_blocks");
+    vst_revnet* n = new (std::nothrow) vst_revnet();
+    VST_REQUIRE(n, "out of host memory");
+    n->cfg = *cfg;
+    n->c0 = cfg->n_channels[0];
+    int c = n->c0;
+    for (int s = 0; s < cfg->n_stages; ++s) {
+        const int ch = cfg->n_channels[s], st = cfg->n_strides[s];
+        bool ok = (st == 1 || st == 2) && cfg->n_blocks[s] >= 1 && ch % cfg->mult == 0 && ch / cfg->mult >= 1 &&
+                  ((st == 1 && ch == c) || (st == 2 && ch == 4 * c));
+        if (!ok) {
+            delete n;
+            set_error("stage %d: channels %d / stride %d inconsistent with incoming half-state width %d", s, ch, st, c);
+            return 2;
+        }
+        for (int i = 0; i < cfg->n_blocks[s]; ++i) add_block(n, n->stack, ch, i == 0 ? st : 1);
+        n->down *= st;
+        c = ch;
+    }
+    n->c_last = c;
+    n->cr_channel = cfg->hidden_dim;
+    for (int i = 0; i < cfg->sp_steps; ++i) n->cr_channel *= 4;
+    if (cfg->in_channel < 1 || cfg->in_channel > n->c0 || n->cr_channel < c || n->cr_channel % cfg->mult != 0 ||
+        (2 * n->cr_channel) % (1 << (2 * cfg->sp_steps)) != 0) {
+        delete n;
+        set_error("unsupported in_channel=%d / hidden_dim=%d / sp_steps=%d for last width %d", cfg->in_channel,
+                  cfg->hidden_dim, cfg->sp_steps, c);
+        return 2;
+    }
+    for (int i = 0; i < cfg->n_cr_blocks; ++i) add_block(n, n->cr, n->cr_channel, 1);
+    *out = n;
+    return 0;
+}
+
+extern "C" void vst_revnet_destroy(vst_revnet* net) { delete net; }
+
+extern "C" int vst_revnet_set_precision(vst_revnet* net, int mode) {
+    VST_REQUIRE(net, "null net");
+    VST_REQUIRE(mode == VST_CONV_FP32, "precision mode %d not available in this build", mode);
+    net->precision = mode;
+    return 0;
+}
+extern "C" int vst_revnet_latent_channels(const vst_revnet* net) { return net ? 2 * net->cfg.hidden_dim : -1; }
+extern "C" int vst_revnet_down_scale(const vst_revnet* net) { return net ? net->down : -1; }
+extern "C" size_t vst_revnet_param_floats(const vst_revnet* net) { return net ? net->raw_floats : 0; }
+extern "C" size_t vst_revnet_packed_bytes(const vst_revnet* net) { return net ? net->packed_floats * sizeof(float) : 0; }
+
+extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, void* packed, void* stream) {
+    VST_REQUIRE(net && raw && packed, "vst_revnet_pack_weights: null argument");
+    VST_REQUIRE(((uintptr_t)packed & 15) == 0, "packed buffer must be 16-byte aligned");
+    float* pk = (float*)packed;
+    for (const std::vector<BlockDesc>* lst : {&net->stack, &net->cr})
+        for (const BlockDesc& b : *lst)
+            for (int k = 0; k < 3; ++k) {
+                const ConvDesc& c = b.conv[k];
+                if (launch_pack_conv_weights(raw + c.raw_w, raw + c.raw_b, pk + c.pk_w, pk + c.pk_b, c.Cin, c.Cout,
+                                             c.CoutPad, (cudaStream_t)stream))
+                    return 1;
+            }
+    return 0;
+}
+
+extern "C" size_t vst_revnet_workspace_bytes(const vst_revnet* net, int B, int H, int W) {
+    (void)B;
+    if (!net || H <= 0 || W <= 0) return 0;
+    return (3 * half_state_floats(net, H, W) + 2 * temp_floats(net, H, W)) * sizeof(float);
+}
+
+static int check_hw(const vst_revnet* net, int B, int H, int W) {
+    VST_REQUIRE(B >= 1, "batch must be >= 1");
+    VST_REQUIRE(H > 0 && W > 0 && H % net->down == 0 && W % net->down == 0,
+                "H, W must be positive multiples of down_scale=%d (got %dx%d)", net->down, H, W);
+    VST_REQUIRE(H / net->down >= 2 && W / net->down >= 2, "image too small for reflection padding at 1/%d resolution",
+                net->down);
+    return 0;
+}
+
+extern "C" int vst_revnet_forward(const vst_revnet* net, const void* packed, const float* x, float* z, int B, int H,
+                                  int W, void* workspace, size_t workspace_bytes, void* stream) {
+    VST_REQUIRE(net && packed && x && z, "vst_revnet_forward: null argument");
+    if (int r = check_hw(net, B, H, W)) return r;
+    Workspace ws;
+    if (int r = carve(net, H, W, workspace, workspace_bytes, &ws)) return r;
+    const size_t xs = (size_t)net->cfg.in_channel * H * W;
+    const size_t zs = (size_t)2 * net->cr_channel * (H / net->down) * (W / net->down);
+    for (int b = 0; b < B; ++b)
+        if (forward_one(net, (const float*)packed, x + b * xs, z + b * zs, H, W, ws, (cudaStream_t)stream)) return 1;
+    return 0;
+}
+
+extern "C" int vst_revnet_inverse(const vst_revnet* net, const void* packed, const float* z, float* x, int B, int H,
+                                  int W, void* workspace, size_t workspace_bytes, void* stream) {
+    VST_REQUIRE(net && packed && x && z, "vst_revnet_inverse: null argument");
+    if (int r = check_hw(net, B, H, W)) return r;
+    Workspace ws;
+    if (int r = carve(net, H, W, workspace, workspace_bytes, &ws)) return r;
+    const size_t xs = (size_t)net->cfg.in_channel * H * W;
+    const size_t zs = (size_t)2 * net->cr_channel * (H / net->down) * (W / net->down);
+    for (int b = 0; b < B; ++b)
+        if (inverse_one(net, (const float*)packed, z + b * zs, x + b * xs, H, W, ws, (cudaStream_t)stream)) return 1;
+    return 0;
+}
