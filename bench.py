@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native CAP-VSTNet stylization hot path.
+
+Workload (BASELINE.json configs[3], the one `metric` is quoted on): photorealistic 1080p video,
+random-init RevResNet (seed 0), synthetic frames, the style image encoded and its cWCT statistics
+hoisted once (rank 0) and NCCL-broadcast; every rank then stylizes its own frames.  A *step* is
+one 1920x1080 frame per rank: encode -> cWCT stats/factor/apply -> decode.  `value` is whole-job
+frames/s with frames resident in HBM; `e2e` is the same through `VideoStylizer.stylize_host`
+with HOST buffers (pinned fp32 frame H2D + uint8 result D2H inside the timed region).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 1080, 1920
+FRAMES_PER_VIDEO = 240
+CONV_FLOP_PER_PX = 609984.0      # 96 convs per pass, 2*MAC
+METRIC = "1080p video frames/s"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(f):
+        try:
+            d = json.load(open(f))
+            p.update({k: float(d[k]) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in d})
+            p["source"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (a torch-fp32 port of the reference path) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_frames_per_s(h, w, steps, warmup, threads):
+    """Time `steps` hoisted-style frames of h x w on the CPU oracle; returns (frames/s at h x w, seconds/frame)."""
+    import torch
+    from oracle import vst_oracle as O
+    from vstnet_b200 import RevResNet
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = RevResNet(hidden_dim=16, sp_steps=2)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(99)
+    style = torch.rand(1, 3, h, w, generator=g)
+    frames = [torch.rand(1, 3, h, w, generator=g) for _ in range(2)]
+    with torch.no_grad():
+        zs = O.revnet_forward(sd, style)                      # hoisted, untimed (as in our arm)
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            zc = O.revnet_forward(sd, frames[i % 2])
+            y = O.revnet_inverse(sd, O.cwct_transfer(zc, zs))
+            float(y[0, 0, 0, 0])
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    spf = sum(ts) / len(ts)
+    return 1.0 / spf, spf
+
+
+def bounded_cpu_sample(budget_s, steps, warmup, threads):
+    """Pick a sub-frame (same aspect, multiple of 4) so (steps+warmup) CPU frames fit `budget_s`;
+    cost is linear in pixels, so frames/s at 1080p = measured frames/s * (h*w)/(1080*1920)."""
+    _, spf = cpu_frames_per_s(272, 480, 1, 1, threads)          # calibration on ~1/16 of the pixels
+    full = spf * (H * W) / (272.0 * 480.0)
+    frac = min(1.0, budget_s / max(1e-9, full * (steps + warmup)))
+    scale = frac ** 0.5
+    h = max(64, int(H * scale) // 4 * 4)
+    w = max(64, int(W * scale) // 4 * 4)
+    if frac >= 1.0:
+        h, w = H, W
+    fps, spf = cpu_frames_per_s(h, w, steps, warmup, threads)
+    pix = (h * w) / float(H * W)
+    return fps * pix, "%d frame(s) of %dx%d (%.1f%% of a 1080p frame's pixels, scaled linearly), %.2f s each" % (
+        steps, w, h, 100 * pix, spf), h, w
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    value, sample, h, w = bounded_cpu_sample(150.0, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg4 photorealistic video 1920x1080, style hoisted, random-init RevResNet",
+                   "frames_per_video": FRAMES_PER_VIDEO},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is Python and cannot travel to the GPU box; this is oracle/vst_oracle.py, the same "
+                "torch CPU ops (F.conv2d, linalg.cholesky) the reference issues, on all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vstnet_b200 import RevResNet, cWCT, _lib
+    from vstnet_b200.video import VideoStylizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K = args.steps if args.steps is not None else max(1, FRAMES_PER_VIDEO // world // 4)
+    Wm = args.warmup if args.warmup is not None else 3
+
+    torch.manual_seed(0)
+    net = RevResNet(hidden_dim=16, sp_steps=2, precision=args.precision).to(dev).eval()
+    vs = VideoStylizer(net, cWCT())
+    gen = torch.Generator(device=dev)
+    style = None
+    if rank == 0:
+        style = torch.rand(1, 3, H, W, device=dev, generator=gen.manual_seed(4321))
+    vs.set_style(style)                               # rank 0 encodes + factorises, one broadcast
+    pool = 4                                          # distinct resident frames cycled through
+    frames = [torch.rand(1, 3, H, W, device=dev, generator=gen.manual_seed(1234 + rank * pool + i)) for i in range(pool)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    for i in range(Wm):
+        vs.stylize(frames[i % pool])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        y = vs.stylize(frames[i % pool])
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - n0
+    _lib.profile_enable(False)
+    prof = _lib.profile_collect()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = world * K / (ms / 1e3)
+
+    # ---- end to end through the host-buffer API (`e2e`)
+    host_frames = [f.cpu().pin_memory() for f in frames[:2]]
+    for i in range(min(Wm, 2)):
+        vs.stylize_host(host_frames[i % 2])
+    barrier()
+    Ke = K
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(Ke):
+        out_host = vs.stylize_host(host_frames[i % 2])
+    t1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_e = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * Ke / (float(ms_e.item()) / 1e3)
+    h2d = host_frames[0].numel() * 4
+    d2h = out_host.numel()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from the live per-launch events of the timed region
+    pk = peaks()
+    kernels = []
+    for name, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        per = d["ms"] / max(1, d["launches"])
+        kernels.append({"kernel": name, "ms_total": round(d["ms"], 3), "launches": d["launches"],
+                        "share": round(d["ms"] / ms, 4),
+                        "tflops": round(d["flops"] / d["ms"] / 1e9, 2) if d["ms"] > 0 else None,
+                        "gbs": round(d["bytes"] / d["ms"] / 1e6, 1) if d["ms"] > 0 else None,
+                        "ms_per_launch": round(per, 4)})
+    top_name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    ai = top["flops"] / max(1.0, top["bytes"])
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tf):
+        try:
+            traffic = json.load(open(tf)).get(top_name)
+        except Exception:
+            traffic = None
+    if ai > pk["bf16_tflops_sustained"] * 1e3 / pk["hbm_gbs"] / 4:      # above the TF32 ridge -> tensor bound
+        ach = top["flops"] / top["ms"] / 1e9
+        roof = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
+                "peak_source": pk["source"] + " bf16 dense sustained (tf32 peak is half of it)"}
+    else:
+        ach = top["bytes"] / top["ms"] / 1e6
+        roof = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"]}
+    roof["launches"] = top["launches"]
+    roof["ms_per_launch"] = top["ms"] / max(1, top["launches"])
+
+    # ---- CPU baseline (rank 0, N == 1 only): the oracle on the host cores, bounded sample
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, sample, _, _ = bounded_cpu_sample(25.0, 1, 1, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": {"workload": "cfg4 photorealistic video 1920x1080, style hoisted + broadcast, random-init RevResNet",
+                   "frames_per_video": FRAMES_PER_VIDEO, "frames_per_step_per_gpu": 1, "conv_precision": args.precision,
+                   "l2": "per-frame working set (~1.5 GB of states) >> 126 MB L2; %d distinct frames cycled" % pool,
+                   "parallelism": "frames sharded dp%d, no data-path collective" % world},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "useful_conv_tflops": 2 * CONV_FLOP_PER_PX * H * W * world * K / (ms / 1e3) / 1e12,
+        "kernels": kernels[:12],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps is None:
+            args.steps = 3
+        if args.warmup is None:
+            args.warmup = 1
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,20 @@ int vst_version(void);
  * "gpu_launches" and for tests that prove the CUDA path ran). */
 unsigned long long vst_launch_count(void);
 
+/* Optional per-launch device timing (CUDA events on the launch stream), aggregated by kernel
+ * class.  bench.py enables it to report the live per-kernel durations its roofline is built on.
+ * vst_profile_collect synchronises on the recorded events, fills up to max_entries entries and
+ * clears the log.  flops / bytes are the ALGORITHMIC figures of DESIGN.md, summed over launches. */
+typedef struct vst_profile_entry {
+    char name[40];
+    double ms;
+    long long launches;
+    double flops;
+    double bytes;
+} vst_profile_entry;
+int vst_profile_enable(int on);
+int vst_profile_collect(vst_profile_entry* out, int max_entries, int* n_out);
+
 /* -------------------------------------------------------------------------------------------
  * RevResNet  — replaces models/RevResNet.py:166-239 (class RevResNet, _forward, _inverse),
  *              :68-116 (residual_block), :119-163 (channel_reduction), :19-43 (pad / squeeze).

@@ -24,6 +24,17 @@ def dev():
     return torch.device("cuda:0")
 
 
+def assert_roundtrip_at_reference_level(xr, xr_ref, x):
+    """Round trip must be no worse than the reference's own on the same input.  Both are pure fp32
+    rounding noise (a handful of ulps), so the max over a small image fluctuates by an ulp or two
+    between summation orders; the comparison is therefore made on the mean error (a stable statistic,
+    must not exceed the reference's by more than 5 %) plus a 2-ulp allowance on the max."""
+    e, e_ref = (xr - x).abs(), (xr_ref - x).abs()
+    ulp = 2.0 ** -24
+    assert float(e.mean()) <= 1.05 * float(e_ref.mean()) + 1e-9, (float(e.mean()), float(e_ref.mean()))
+    assert float(e.max()) <= float(e_ref.max()) + 2 * ulp, (float(e.max()), float(e_ref.max()))
+
+
 def maxdiff(a, b):
     return float((a.detach().cpu().double() - torch.as_tensor(b).double()).abs().max())
 
@@ -42,7 +53,7 @@ def test_revnet_vs_golden(dev, mode, bias_seed):
     xd = net(torch.from_numpy(g["z_rand"]).to(dev), forward=False)
     assert maxdiff(xd, g["x_dec"]) <= OP_TOL
     xr = net(z, forward=False)
-    assert maxdiff(xr, g["x"]) <= max(float(g["roundtrip_err"]), 3e-7)
+    assert_roundtrip_at_reference_level(xr.cpu(), torch.from_numpy(g["x_roundtrip"]), torch.from_numpy(g["x"]))
 
 
 @pytest.mark.parametrize("mode,h,w,b", [("photo", 40, 72, 1), ("art", 36, 44, 2), ("photo", 8, 8, 1),
@@ -59,8 +70,7 @@ def test_revnet_vs_oracle_odd_sizes(dev, mode, h, w, b):
     z = net(x.to(dev))
     assert maxdiff(z, zr) <= OP_TOL
     xr = net.inverse(z)
-    ref_rt = float((xr_ref - x).abs().max())
-    assert maxdiff(xr, x) <= max(ref_rt, 3e-7), "round trip worse than the reference's own (%g)" % ref_rt
+    assert_roundtrip_at_reference_level(xr.cpu(), xr_ref, x)
     assert not z.requires_grad
 
 

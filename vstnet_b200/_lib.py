@@ -33,11 +33,18 @@ class RevnetConfig(C.Structure):
     ]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms", C.c_double), ("launches", C.c_longlong), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/vstb200.h declares
 SIGNATURES = {
     "vst_last_error": (C.c_char_p, []),
     "vst_version": (C.c_int, []),
     "vst_launch_count": (C.c_ulonglong, []),
+    "vst_profile_enable": (C.c_int, [C.c_int]),
+    "vst_profile_collect": (C.c_int, [C.POINTER(ProfileEntry), C.c_int, C.POINTER(C.c_int)]),
     "vst_revnet_create": (C.c_int, [C.POINTER(RevnetConfig), C.POINTER(C.c_void_p)]),
     "vst_revnet_destroy": (None, [C.c_void_p]),
     "vst_revnet_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
@@ -95,3 +102,16 @@ def check(rc, what):
 
 def launch_count():
     return int(load().vst_launch_count())
+
+
+def profile_enable(on):
+    check(load().vst_profile_enable(1 if on else 0), "vst_profile_enable")
+
+
+def profile_collect(max_entries=128):
+    """-> {kernel class: dict(ms, launches, flops, bytes)}; synchronises on the recorded events."""
+    arr = (ProfileEntry * max_entries)()
+    n = C.c_int(0)
+    check(load().vst_profile_collect(arr, max_entries, C.byref(n)), "vst_profile_collect")
+    return {arr[i].name.decode(): dict(ms=arr[i].ms, launches=int(arr[i].launches), flops=arr[i].flops,
+                                       bytes=arr[i].bytes) for i in range(n.value)}

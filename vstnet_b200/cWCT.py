@@ -132,6 +132,54 @@ class cWCT(nn.Module):
                 self._apply(content[i], out[i], N, n, None, 1, T, mu, beta, valid, st)
         return out
 
+    # ------------------------------------------------------------------ style hoisting (video)
+    @torch.no_grad()
+    def precompute_style(self, style_feat, smask=None):
+        """Style statistics computed once per video instead of once per frame (the reference
+        re-encodes and re-factorises the style every frame, video_transfer.py:195).
+
+        Returns an opaque dict whose ``stats`` tensors (one uint8 device buffer per sample) can be
+        ``torch.distributed.broadcast`` to the other ranks as they are."""
+        _check_feat(style_feat, "style_feat")
+        B, N, sH, sW = style_feat.shape
+        dev = style_feat.device
+        style = style_feat.contiguous()
+        ns = sH * sW
+        stats, L = [], 1
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            if smask is not None:
+                masks = [self._mask_to_device(smask[i], ns, dev, "smask") for i in range(B)]
+                L = min(max(mx for _, mx in masks) + 1, 255)
+            for i in range(B):
+                stats.append(self._stats(style[i], N, ns, masks[i][0] if smask is not None else None, L, st))
+        return {"stats": stats, "L": L, "masked": smask is not None, "C": N}
+
+    @torch.no_grad()
+    def transfer_precomputed(self, content_feat, style_pre, cmask=None, alpha_c=0.0, out=None):
+        """``transfer`` / ``interpolation`` (one style) against hoisted style statistics."""
+        _check_feat(content_feat, "content_feat")
+        B, N, cH, cW = content_feat.shape
+        if N != style_pre["C"] or len(style_pre["stats"]) != B:
+            raise ValueError("style statistics were computed for a different shape")
+        if style_pre["masked"] != (cmask is not None):
+            raise ValueError("content and style masks must both be given or both be None")
+        dev = content_feat.device
+        content = content_feat.contiguous()
+        masked, L = style_pre["masked"], style_pre["L"]
+        if out is None:
+            out = content if masked else torch.empty_like(content)
+        n = cH * cW
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for i in range(B):
+                cm = self._mask_to_device(cmask[i], n, dev, "cmask")[0] if masked else None
+                cst = self._stats(content[i], N, n, cm, L, st)
+                T, mu, beta, valid = self._factor(cst, [style_pre["stats"][i]], [1.0], 0.0 if masked else alpha_c, N, L,
+                                                  masked, dev, st)
+                self._apply(content[i], out[i], N, n, cm, L, T, mu, beta, valid, st)
+        return out
+
     @torch.no_grad()
     def _transfer_seg(self, content_feat, style_feat, cmask, smask):
         """Per-label masked transfer (ref: cWCT.py:49-109).  Mutates and returns content_feat."""

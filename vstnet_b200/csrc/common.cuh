@@ -48,4 +48,20 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 int num_sms();
 
+// ---- optional per-launch device timing (cudaEvent pairs on the launch stream), aggregated by
+// kernel class; enabled by bench.py to obtain the live per-kernel durations of the roofline.
+bool prof_on();
+void prof_begin(cudaStream_t st, const char* cls, double flops, double bytes);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    bool on;
+    ProfScope(cudaStream_t s, const char* cls, double flops, double bytes) : st(s), on(prof_on()) {
+        if (on) prof_begin(st, cls, flops, bytes);
+    }
+    ~ProfScope() {
+        if (on) prof_end(st);
+    }
+};
+
 }  // namespace vst

@@ -175,6 +175,12 @@ static int launch_cfg(const ConvArgs& a, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid(cdiv(a.Wout, Cfg::TW), cdiv(a.Hout, Cfg::TH), cdiv(a.Cout, Cfg::CT));
+    char cls[40];
+    snprintf(cls, sizeof(cls), "conv3x3_ffma %d>%d s%d", a.Cin, a.Cout, S);
+    const double px = (double)a.Hout * a.Wout;
+    const bool coupled = a.epi >= EPI_ADD;
+    ProfScope prof(st, cls, 2.0 * 9 * a.Cin * a.Cout * px,
+                   4.0 * ((double)a.Cin * a.Hin * a.Win + (coupled ? 2.0 : 1.0) * a.Cout * px));
     kern<<<grid, 256, Cfg::SMEM, st>>>(a);
     return check_launch("conv3x3_ffma");
 }
@@ -236,11 +242,13 @@ static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 
 
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st) {
     size_t total = (size_t)C * Hin * Win;
+    ProfScope prof(st, "space_to_depth", 0.0, 8.0 * total);
     space_to_depth_kernel<<<ew_grid(total), 256, 0, st>>>(in, out, C, Hin / 2, Win / 2);
     return check_launch("space_to_depth");
 }
 int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Win, cudaStream_t st) {
     size_t total = (size_t)4 * Cout * Hin * Win;
+    ProfScope prof(st, "depth_to_space", 0.0, 8.0 * total);
     depth_to_space_kernel<<<ew_grid(total), 256, 0, st>>>(in, out, Cout, Hin, Win);
     return check_launch("depth_to_space");
 }
@@ -271,11 +279,13 @@ __global__ void latent_spread_kernel(float* __restrict__ x1, float* __restrict__
 
 int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st) {
     size_t total = (size_t)2 * Ch * h * w;
+    ProfScope prof(st, "latent_spread", 0.0, 8.0 * total);
     latent_spread_kernel<true><<<ew_grid(total), 256, 0, st>>>(const_cast<float*>(x1), const_cast<float*>(x2), z, Ch, h, w, L);
     return check_launch("latent_spread");
 }
 int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, cudaStream_t st) {
     size_t total = (size_t)2 * Ch * h * w;
+    ProfScope prof(st, "latent_gather", 0.0, 8.0 * total);
     latent_spread_kernel<false><<<ew_grid(total), 256, 0, st>>>(x1, x2, const_cast<float*>(z), Ch, h, w, L);
     return check_launch("latent_gather");
 }

@@ -548,6 +548,8 @@ static int launch_apply(const float* feat, float* out, int C, long long n, const
     }
     long long tiles = (n + Cfg::PX - 1) / Cfg::PX;
     int grid = (int)std::min<long long>(tiles, (long long)num_sms() * (CP == 32 ? 4 : 2));
+    ProfScope prof(st, CP == 32 ? "cwct_apply c32" : "cwct_apply c128", 2.0 * C * C * (double)n,
+                   8.0 * C * (double)n + (labels ? (double)n : 0.0));
     kern<<<grid, 256, Cfg::SMEM, st>>>(feat, out, C, n, labels, L, T, mu, beta, valid, tiles);
     return check_launch("cwct_apply");
 }
@@ -576,6 +578,8 @@ extern "C" int vst_cwct_stats(const float* feat, int C, long long n, const uint8
     pivot_kernel<<<C, 256, 0, st>>>(feat, n, sv.pivot);
     if (check_launch("cwct_pivot")) return 1;
     const int sms = num_sms();
+    ProfScope prof(st, C <= 32 ? "cwct_gram c32" : "cwct_gram c128", 2.0 * C * C * (double)n,
+                   4.0 * C * (double)n + (labels ? (double)n : 0.0));
     if (C <= 32) {
         int grid = sms * 3;
         long long warps = (long long)grid * 8;
@@ -618,6 +622,7 @@ extern "C" int vst_cwct_factor(const void* content_stats, const void* const* sty
         VST_CUDA_OK(cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (128 * 129 / 2) * 8 + 2 * 128 * 8));
         attr_set = true;
     }
+    ProfScope prof((cudaStream_t)stream, "cwct_factor", 0.0, 0.0);
     factor_kernel<<<n_labels, 256, smem, (cudaStream_t)stream>>>(fa);
     return check_launch("cwct_factor");
 }

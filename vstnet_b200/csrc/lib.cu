@@ -1,5 +1,8 @@
 // lib.cu — library-level state: last-error string, launch counter, device properties.
 #include <string.h>
+#include <vector>
+#include <mutex>
+#include <utility>
 #include "common.cuh"
 
 namespace vst {
@@ -26,7 +29,70 @@ int num_sms() {
     return cached[dev];
 }
 
+// ------------------------------------------------------------------------------------------
+// per-launch profiler
+// ------------------------------------------------------------------------------------------
+struct ProfRec {
+    char cls[40];
+    cudaEvent_t a, b;
+    double flops, bytes;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pool;
+static std::mutex g_prof_mu;
+
+bool prof_on() { return g_prof; }
+
+void prof_begin(cudaStream_t st, const char* cls, double flops, double bytes) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    snprintf(r.cls, sizeof(r.cls), "%s", cls);
+    if (!g_pool.empty()) {
+        r.a = g_pool.back().first; r.b = g_pool.back().second; g_pool.pop_back();
+    } else {
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    }
+    r.flops = flops; r.bytes = bytes;
+    cudaEventRecord(r.a, st);
+    g_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, st);
+}
+
 }  // namespace vst
+
+extern "C" int vst_profile_enable(int on) {
+    vst::g_prof = on != 0;
+    return 0;
+}
+extern "C" int vst_profile_collect(vst_profile_entry* out, int max_entries, int* n_out) {
+    using namespace vst;
+    VST_REQUIRE(out && n_out && max_entries > 0, "vst_profile_collect: bad arguments");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int n = 0;
+    for (ProfRec& r : g_recs) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(r.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+        g_pool.push_back({r.a, r.b});
+        if (e != cudaSuccess) continue;
+        int k = 0;
+        for (; k < n; ++k) if (strncmp(out[k].name, r.cls, sizeof(out[k].name)) == 0) break;
+        if (k == n) {
+            if (n == max_entries) continue;
+            memset(&out[n], 0, sizeof(out[n]));
+            snprintf(out[n].name, sizeof(out[n].name), "%s", r.cls);
+            ++n;
+        }
+        out[k].ms += ms; out[k].launches += 1; out[k].flops += r.flops; out[k].bytes += r.bytes;
+    }
+    g_recs.clear();
+    *n_out = n;
+    return 0;
+}
 
 extern "C" const char* vst_last_error(void) { return vst::g_err; }
 extern "C" int vst_version(void) { return 100; }

@@ -1,0 +1,99 @@
+"""Frame-sharded video stylization (the multi-GPU form of the hot path).
+
+Replaces the per-frame loop of the reference's ``video_transfer.py:160-214``.  One process per
+GPU; the style image is encoded and its cWCT statistics computed ONCE (rank 0) and broadcast
+with a single ``torch.distributed.broadcast`` (NCCL over NVLink); every rank then stylizes
+frames ``rank, rank+W, rank+2W, ...`` with no further communication.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .cWCT import cWCT
+from .RevResNet import RevResNet
+
+
+def shard_frames(n_frames, rank, world_size):
+    """Frame indices owned by ``rank`` (rank-strided; every frame has exactly one owner)."""
+    return list(range(rank, n_frames, world_size))
+
+
+class VideoStylizer:
+    def __init__(self, net: RevResNet, cwct: cWCT | None = None, alpha_c=None):
+        self.net = net
+        self.cwct = cwct if cwct is not None else cWCT()
+        self.alpha_c = alpha_c
+        self.style_pre = None
+        self._lib = _lib.load()
+        self._pin = {}
+
+    # ------------------------------------------------------------------ style (once per video)
+    @torch.no_grad()
+    def set_style(self, style=None, style_seg=None, group=None, src=0):
+        """Encode the style image and hoist its statistics; broadcast from ``src`` if a process
+        group is initialised.  Non-source ranks may pass ``style=None`` but must know its shape
+        through the broadcast metadata."""
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        rank = dist.get_rank(group) if distributed else 0
+        dev = next(self.net.parameters()).device
+        if not distributed or rank == src:
+            zs = self.net(style.to(dev), forward=True)
+            pre = self.cwct.precompute_style(zs, style_seg)
+        if distributed:
+            meta = torch.zeros(4, dtype=torch.int64, device=dev)
+            if rank == src:
+                meta[:] = torch.tensor([pre["L"], int(pre["masked"]), pre["C"], len(pre["stats"])])
+            dist.broadcast(meta, src=src, group=group)
+            L, masked, C_, B = (int(v) for v in meta.tolist())
+            nbytes = int(self._lib.vst_cwct_stats_bytes(C_, L))
+            stats = pre["stats"] if rank == src else [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(B)]
+            for s in stats:
+                dist.broadcast(s, src=src, group=group)       # the path's only data collective
+            pre = {"stats": stats, "L": L, "masked": bool(masked), "C": C_}
+        self.style_pre = pre
+        return pre
+
+    # ------------------------------------------------------------------ per frame
+    @torch.no_grad()
+    def stylize(self, content, content_seg=None):
+        """content: fp32 CUDA [1,3,H,W] in [0,1] -> stylized fp32 CUDA [1,3,H,W]
+        (encode -> cWCT vs hoisted style -> decode; ref: video_transfer.py:192-206)."""
+        z = self.net(content, forward=True)
+        a = 0.0 if self.alpha_c is None else float(self.alpha_c)
+        zcs = self.cwct.transfer_precomputed(z, self.style_pre, content_seg, a, out=z)
+        return self.net(zcs, forward=False)
+
+    def _pinned(self, key, shape, dtype):
+        t = self._pin.get(key)
+        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype).pin_memory()
+            self._pin[key] = t
+        return t
+
+    @torch.no_grad()
+    def stylize_host(self, frame, content_seg=None, bgr=False):
+        """End-to-end call with HOST buffers.  ``frame``: pinned-or-not host tensor, either fp32
+        [1,3,H,W] (what ``ToTensor`` gives, video_transfer.py:188) or uint8 [H,W,3].  Returns a
+        pinned uint8 [H,W,3] host tensor (``mul(255).clamp(0,255).byte()`` semantics,
+        video_transfer.py:211-214).  H2D and D2H copies are part of the call."""
+        dev = next(self.net.parameters()).device
+        st = torch.cuda.current_stream(dev)
+        if frame.dtype == torch.uint8:
+            H, W = frame.shape[0], frame.shape[1]
+            u8 = frame.to(dev, non_blocking=True)
+            x = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
+            _lib.check(self._lib.vst_frame_u8_to_f32(u8.data_ptr(), x.data_ptr(), H, W, int(bgr), st.cuda_stream),
+                       "vst_frame_u8_to_f32")
+        else:
+            H, W = frame.shape[2], frame.shape[3]
+            x = frame.to(dev, non_blocking=True)
+        y = self.stylize(x, content_seg)
+        o = torch.empty(H, W, 3, dtype=torch.uint8, device=dev)
+        _lib.check(self._lib.vst_frame_f32_to_u8(y.data_ptr(), o.data_ptr(), H, W, int(bgr), st.cuda_stream),
+                   "vst_frame_f32_to_u8")
+        host = self._pinned("out", (H, W, 3), torch.uint8)
+        host.copy_(o, non_blocking=True)
+        st.synchronize()
+        return host
