@@ -29,6 +29,13 @@ int launch_pack_conv_weights(const float* w, const float* b, float* wp, float* b
                              cudaStream_t st);
 int launch_conv3x3_ffma(const ConvArgs& a, int stride, cudaStream_t st);
 
+// tensor-core (tcgen05) path, conv_tc.cu
+bool tc_eligible(int Cin, int Cout, int stride);
+int tc_tile_n(int Cout);
+size_t tc_packed_floats(int Cin, int Cout, int N, int terms);
+int launch_pack_tc_weights(const float* w, float* wp, int Cin, int Cout, int N, int terms, cudaStream_t st);
+int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st);
+
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st);
 int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Win, cudaStream_t st);
 int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st);

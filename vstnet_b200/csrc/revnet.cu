@@ -17,6 +17,8 @@ struct ConvDesc {
     int Cin, Cout, CoutPad, stride;
     size_t raw_w, raw_b;  // float offsets into the flat raw parameter buffer
     size_t pk_w, pk_b;    // float offsets into the packed buffer
+    bool tc;              // eligible for the tcgen05 implicit-GEMM kernel
+    size_t pk_tc;         // float offset of the tensor-core weight pack (sized for hi+lo terms)
 };
 struct BlockDesc {
     int channel, stride;
@@ -53,6 +55,9 @@ static void add_block(vst_revnet* n, std::vector<BlockDesc>& dst, int channel, i
         c.raw_b = n->raw_floats; n->raw_floats += (size_t)c.Cout;
         c.pk_w = n->packed_floats; n->packed_floats += (size_t)c.Cin * 9 * c.CoutPad;
         c.pk_b = n->packed_floats; n->packed_floats += (size_t)c.CoutPad;
+        c.tc = tc_eligible(c.Cin, c.Cout, c.stride);
+        c.pk_tc = n->packed_floats;
+        if (c.tc) n->packed_floats += tc_packed_floats(c.Cin, c.Cout, tc_tile_n(c.Cout), 3);
     }
     dst.push_back(b);
 }
@@ -104,14 +109,28 @@ static ConvArgs conv_args(const ConvDesc& c, const float* packed, const float* i
     return a;
 }
 
+static int tc_terms(int precision) {
+    return precision == VST_CONV_TF32 ? 1 : precision == VST_CONV_TF32X2 ? 2 : precision == VST_CONV_TF32X3 ? 3 : 0;
+}
+
+static int run_conv(const vst_revnet* n, const ConvDesc& c, const float* packed, const float* in, int Hin, int Win,
+                    float* out, const float* res, int epi, cudaStream_t st) {
+    ConvArgs a = conv_args(c, packed, in, Hin, Win, out, res, epi);
+    const int terms = tc_terms(n->precision);
+    if (terms > 0 && c.tc) {
+        a.w = packed + c.pk_tc;
+        return launch_conv3x3_tc(a, terms, st);
+    }
+    return launch_conv3x3_ffma(a, c.stride, st);
+}
+
 // F(x) = conv3(relu(conv2(relu(conv1(x)))))  with the coupling fused into conv3's epilogue
 static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, const float* x, int Hin, int Win,
                  const Workspace& ws, const float* res, float* out, int epi, cudaStream_t st) {
     const int Ho = Hin / b.stride, Wo = Win / b.stride;
-    (void)n;
-    if (launch_conv3x3_ffma(conv_args(b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU), b.stride, st)) return 1;
-    if (launch_conv3x3_ffma(conv_args(b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU), 1, st)) return 1;
-    if (launch_conv3x3_ffma(conv_args(b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi), 1, st)) return 1;
+    if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, st)) return 1;
+    if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, st)) return 1;
+    if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, st)) return 1;
     return 0;
 }
 
@@ -229,7 +248,7 @@ extern "C" void vst_revnet_destroy(vst_revnet* net) { delete net; }
 
 extern "C" int vst_revnet_set_precision(vst_revnet* net, int mode) {
     VST_REQUIRE(net, "null net");
-    VST_REQUIRE(mode == VST_CONV_FP32, "precision mode %d not available in this build", mode);
+    VST_REQUIRE(mode >= VST_CONV_FP32 && mode <= VST_CONV_TF32, "unknown precision mode %d", mode);
     net->precision = mode;
     return 0;
 }
@@ -248,6 +267,11 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
                 const ConvDesc& c = b.conv[k];
                 if (launch_pack_conv_weights(raw + c.raw_w, raw + c.raw_b, pk + c.pk_w, pk + c.pk_b, c.Cin, c.Cout,
                                              c.CoutPad, (cudaStream_t)stream))
+                    return 1;
+                const int terms = tc_terms(net->precision);
+                if (terms > 0 && c.tc &&
+                    launch_pack_tc_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, tc_tile_n(c.Cout), terms,
+                                           (cudaStream_t)stream))
                     return 1;
             }
     return 0;
