@@ -125,12 +125,12 @@ class RevResNet(nn.Module):
         return 2 * self.hidden_dim
 
     def __del__(self):
-        h, self._h = getattr(self, "_h", None), None
-        if h:
-            try:
-                self._lib.vst_revnet_destroy(h)
-            except Exception:
-                pass
+        try:
+            h = self.__dict__.pop("_h", None)
+            if h:
+                self.__dict__["_lib"].vst_revnet_destroy(h)
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ device-side state
     def _packed_weights(self, device):

@@ -1,0 +1,286 @@
+// block16.cu — one whole reversible block of the full-resolution stage in ONE kernel (CUDA-core fp32).
+//
+// Replaces residual_block.forward / .inverse (models/RevResNet.py:96-116) for channel = 16,
+// mult = 4, stride = 1:   out = res +/- conv3(relu(conv2(relu(conv1(refpad(x))))))
+// with 16 -> 4 -> 4 -> 16 channels, a ReflectionPad2d(1) before every conv (:79-88).
+//
+// Why not tensor cores: N = 4 output channels is below the tcgen05 minimum and the stage is
+// HBM-bound anyway (13.5 FLOP/B); what matters is that the 4-channel intermediates
+// never touch HBM.  A CTA owns a 28x28 output tile: it stages the 34x34x16 input halo tile in
+// shared memory, computes conv1 on 32x32, conv2 on 30x30, conv3 on 28x28, and reads/writes the
+// coupling operand once.  HBM traffic per block: x read once (+halo), res read once, out written
+// once — 3 half-states instead of the 4+ of three separate conv launches.
+//
+// Reflection inside the fused tile: intermediates exist only at in-image positions; after each
+// conv the tile positions that stand for image row/col -1 or H/W are overwritten with their
+// mirror (row 1 / H-2), which is exactly what the next ReflectionPad2d(1) would read.
+//
+// Data path: the input halo tile arrives by TMA bulk copies (one 544-byte segment per group and
+// row, straight from the P4 tensor, completion on an mbarrier) and stays 4-channel interleaved in
+// shared memory, as do the two intermediates, so every shared-memory access is a conflict-free
+// 16-byte vector.  Thread mapping: 4 warps; lane = tile column, each warp owns a band of rows and
+// every thread a vertical strip of that band (a 10-row register window per kx serves the three
+// ky taps), all output channels of a pass in registers.  Weights sit in shared memory in the
+// [cin][tap][cout] layout of conv_direct.cu's pack and are read as warp-uniform float4 broadcasts.
+#include "kernels.cuh"
+
+namespace vst {
+
+namespace b16 {
+constexpr int TO = 28;   // output tile edge
+constexpr int T1 = 32;   // conv1 tile edge (TO + 4) == warp width
+constexpr int T2 = 30;   // conv2 tile edge
+constexpr int XT = 34;   // input tile edge
+constexpr int T2_PITCH = 32;
+constexpr int XS_F4 = 4 * XT * XT;     // input halo tile, [group][row][col] float4 (4 channels per element)
+constexpr int T1_F4 = T1 * T1;         // [row][col] float4 (the 4 bottleneck channels)
+constexpr int W_FLOATS = 16 * 9 * 4 + 4 + 4 * 9 * 4 + 4 + 4 * 9 * 16 + 16;
+constexpr size_t SMEM = (size_t)(XS_F4 + T1_F4) * 16 + (size_t)W_FLOATS * 4 + 16;
+}  // namespace b16
+
+__device__ __forceinline__ uint32_t b16_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// overwrite the tile rows/cols that stand for image row/col -1 and H/W with their mirrors.
+// tile(r, c) <-> image(oy + r, ox + c); square tile of edge n, row pitch `pitch` (float4 elements).
+__device__ __forceinline__ void tile_reflect(float4* t, int n, int pitch, int oy, int ox, int H, int W, int tid) {
+    {
+        const int rm = -1 - oy, rs = 1 - oy;            // row -1 <- row 1
+        if (rm >= 0 && rs < n)
+            for (int c = tid; c < n; c += 128) t[rm * pitch + c] = t[rs * pitch + c];
+        const int rH = H - oy, rS = H - 2 - oy;         // row H <- row H-2
+        if (rH < n && rS >= 0)
+            for (int c = tid; c < n; c += 128) t[rH * pitch + c] = t[rS * pitch + c];
+    }
+    __syncthreads();
+    {
+        const int cm = -1 - ox, cc = 1 - ox;
+        if (cm >= 0 && cc < n)
+            for (int r = tid; r < n; r += 128) t[r * pitch + cm] = t[r * pitch + cc];
+        const int cW = W - ox, cS = W - 2 - ox;
+        if (cW < n && cS >= 0)
+            for (int r = tid; r < n; r += 128) t[r * pitch + cW] = t[r * pitch + cS];
+    }
+    __syncthreads();
+}
+
+#define B16_FMA4(ACC, XV, WV)                 \
+    ACC[0] = fmaf(XV, WV.x, ACC[0]);          \
+    ACC[1] = fmaf(XV, WV.y, ACC[1]);          \
+    ACC[2] = fmaf(XV, WV.z, ACC[2]);          \
+    ACC[3] = fmaf(XV, WV.w, ACC[3]);
+
+__global__ void __launch_bounds__(128, 2) rev_block16_kernel(Block16Args a) {
+    using namespace b16;
+    extern __shared__ __align__(16) float4 sm4[];
+    float4* xs = sm4;                     // [4][34][34]  input halo tile; later reused for t2 [30][32]
+    float4* t1 = sm4 + XS_F4;             // [32][32]
+    float* ws = reinterpret_cast<float*>(t1 + T1_F4);
+    float* w1s = ws;                      // [16][9][4]
+    float* b1s = w1s + 16 * 9 * 4;
+    float* w2s = b1s + 4;                 // [4][9][4]
+    float* b2s = w2s + 4 * 9 * 4;
+    float* w3s = b2s + 4;                 // [4][9][16]
+    float* b3s = w3s + 4 * 9 * 16;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b3s + 16);
+    float4* t2 = xs;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TO, y0 = blockIdx.y * TO;
+    const int H = a.H, W = a.W, Hp = H + 2, Wp = W + 2;
+
+    // ---- input halo tile (image rows y0-3 .. y0+30 = padded rows y0-2 ..): one TMA bulk copy per
+    //      (group, row) segment, straight from the P4 tensor; completion on an mbarrier.
+    const int shift = x0 < 2 ? 2 - x0 : 0;                 // tile columns left of the padded tensor
+    const uint32_t seg_bytes = (uint32_t)(XT - shift) * 16;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b16_smem_u32(bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b16_smem_u32(bar)),
+                         "r"(seg_bytes * 4 * XT) : "memory");
+        const float4* x4 = reinterpret_cast<const float4*>(a.x);
+        for (int i = lane; i < 4 * XT; i += 32) {
+            const int g = i / XT, iy = i - g * XT;
+            const int py = min(max(y0 - 2 + iy, 0), Hp - 1);
+            const float4* src = x4 + ((size_t)g * Hp + py) * Wp + (x0 - 2 + shift);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             b16_smem_u32(xs + (g * XT + iy) * XT + shift)),
+                         "l"(src), "r"(seg_bytes), "r"(b16_smem_u32(bar))
+                         : "memory");
+        }
+    }
+    // ---- weights (conv_direct.cu pack layout [cin][tap][cout]) while the tile is in flight
+    for (int i = tid; i < 16 * 9 * 4; i += 128) { w1s[i] = __ldg(a.w1 + i); w3s[i] = __ldg(a.w3 + i); }
+    for (int i = tid; i < 4 * 9 * 4; i += 128) w2s[i] = __ldg(a.w2 + i);
+    if (tid < 4) { b1s[tid] = __ldg(a.b1 + tid); b2s[tid] = __ldg(a.b2 + tid); }
+    if (tid < 16) b3s[tid] = __ldg(a.b3 + tid);
+    __syncthreads();
+    {
+        const uint32_t ba = b16_smem_u32(bar);
+        uint32_t done = 0;
+        for (uint32_t spin = 0; spin < (1u << 24) && !done; ++spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(ba), "r"(0u) : "memory");
+        if (!done) __trap();
+    }
+
+    // ---- conv1 16 -> 4 on the 32x32 tile: t1(r, c) <-> image (y0-2+r, x0-2+c); warp = 8 rows, lane = col
+    {
+        float acc[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = b1s[c];
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                float4 v[10];
+                const float4* ip = xs + (g * XT + warp * 8) * XT + lane + kx;
+#pragma unroll
+                for (int r = 0; r < 10; ++r) v[r] = ip[r * XT];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const float* wp = w1s + ((4 * g) * 9 + ky * 3 + kx) * 4;
+                    const float4 wa = *reinterpret_cast<const float4*>(wp);
+                    const float4 wb = *reinterpret_cast<const float4*>(wp + 36);
+                    const float4 wc = *reinterpret_cast<const float4*>(wp + 72);
+                    const float4 wd = *reinterpret_cast<const float4*>(wp + 108);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        B16_FMA4(acc[r], v[r + ky].x, wa)
+                        B16_FMA4(acc[r], v[r + ky].y, wb)
+                        B16_FMA4(acc[r], v[r + ky].z, wc)
+                        B16_FMA4(acc[r], v[r + ky].w, wd)
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            t1[(warp * 8 + r) * T1 + lane] = make_float4(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f),
+                                                         fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
+    }
+    __syncthreads();
+    tile_reflect(t1, T1, T1, y0 - 2, x0 - 2, H, W, tid);
+
+    // ---- conv2 4 -> 4 on the 30x30 tile: t2(r, c) <-> image (y0-1+r, x0-1+c); reads t1 rows r..r+2
+    {
+        float acc[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = b2s[c];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            float4 v[10];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) v[r] = t1[min(warp * 8 + r, T1 - 1) * T1 + min(lane + kx, T1 - 1)];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float* wp = w2s + (ky * 3 + kx) * 4;
+                const float4 wa = *reinterpret_cast<const float4*>(wp);
+                const float4 wb = *reinterpret_cast<const float4*>(wp + 36);
+                const float4 wc = *reinterpret_cast<const float4*>(wp + 72);
+                const float4 wd = *reinterpret_cast<const float4*>(wp + 108);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    B16_FMA4(acc[r], v[r + ky].x, wa)
+                    B16_FMA4(acc[r], v[r + ky].y, wb)
+                    B16_FMA4(acc[r], v[r + ky].z, wc)
+                    B16_FMA4(acc[r], v[r + ky].w, wd)
+                }
+            }
+        }
+        // xs is dead (every conv1 read happened before the barriers above): t2 reuses its storage
+        if (lane < T2)
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (warp * 8 + r < T2)
+                    t2[(warp * 8 + r) * T2_PITCH + lane] = make_float4(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f),
+                                                                       fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
+    }
+    __syncthreads();
+    tile_reflect(t2, T2, T2_PITCH, y0 - 1, x0 - 1, H, W, tid);
+
+    // ---- conv3 4 -> 16 on the 28x28 tile, two passes of 8 output channels; warp = 7 rows
+    const int x = x0 + lane;
+    const bool xin = lane < TO && x < W;
+    const float4* res4 = reinterpret_cast<const float4*>(a.res);
+    float4* out4 = reinterpret_cast<float4*>(a.out);
+    const size_t plane = p4_plane_px(H, W);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        // coupling operand first: its global latency hides behind the FMAs below
+        float4 rv[7][2];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const int y = y0 + warp * 7 + r;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                rv[r][j] = (xin && y < H) ? res4[(size_t)(half * 2 + j) * plane + (size_t)(y + 1) * Wp + x + 1]
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float acc[7][8];
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = b3s[half * 8 + c];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            float4 v[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) v[r] = t2[(warp * 7 + r) * T2_PITCH + min(lane + kx, T2 - 1)];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const float* wp = w3s + (ci * 9 + ky * 3 + kx) * 16 + half * 8;
+                    const float4 wa = *reinterpret_cast<const float4*>(wp);
+                    const float4 wb = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        const float xv = ci == 0 ? v[r + ky].x : ci == 1 ? v[r + ky].y : ci == 2 ? v[r + ky].z : v[r + ky].w;
+                        B16_FMA4(acc[r], xv, wa)
+                        B16_FMA4((acc[r] + 4), xv, wb)
+                    }
+                }
+            }
+        }
+        // ---- additive coupling + store (RevResNet.py:103, :110-111)
+        if (xin) {
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
+                const int y = y0 + warp * 7 + r;
+                if (y >= H) continue;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 q = rv[r][j];
+                    float4 o;
+                    if (a.sub) o = make_float4(q.x - acc[r][4 * j], q.y - acc[r][4 * j + 1], q.z - acc[r][4 * j + 2], q.w - acc[r][4 * j + 3]);
+                    else o = make_float4(q.x + acc[r][4 * j], q.y + acc[r][4 * j + 1], q.z + acc[r][4 * j + 2], q.w + acc[r][4 * j + 3]);
+                    p4_store(out4 + (size_t)(half * 2 + j) * plane, H, W, y, x, o);
+                }
+            }
+        }
+    }
+}
+
+int launch_rev_block16(const Block16Args& a, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        VST_CUDA_OK(cudaFuncSetAttribute(rev_block16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b16::SMEM));
+        attr_set = true;
+    }
+    VST_REQUIRE(a.H >= 4 && a.W >= 4, "rev_block16: image too small (%dx%d)", a.H, a.W);
+    dim3 grid(cdiv(a.W, b16::TO), cdiv(a.H, b16::TO));
+    const double px = (double)a.H * a.W;
+    ProfScope prof(st, "rev_block16 (16>4>4>16)", 2.0 * 9 * (16 * 4 + 4 * 4 + 4 * 16) * px, 3.0 * 64.0 * px);
+    rev_block16_kernel<<<grid, 128, b16::SMEM, st>>>(a);
+    return check_launch("rev_block16");
+}
+
+}  // namespace vst

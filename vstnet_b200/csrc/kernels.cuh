@@ -5,6 +5,42 @@
 
 namespace vst {
 
+// ------------------------------------------------------------------------------------------
+// "P4" activation layout (every tensor inside the reversible network lives in it):
+//     [C/4][H+2][W+2][4] fp32
+// i.e. groups of 4 channels interleaved per pixel (one pixel of one group = one 16-byte unit)
+// with a 1-pixel border that already holds the ReflectionPad2d(1) values (RevResNet.py:80,83,86).
+// Whoever WRITES a tensor also writes its border (p4_store), so every consumer — in particular
+// the TMA loader of the tcgen05 convolution — reads plain rectangular boxes with no edge cases,
+// and the im2col window of tap (ky,kx) is a 16-byte-granular address shift.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t p4_plane_px(int H, int W) { return (size_t)(H + 2) * (size_t)(W + 2); }
+// floats needed for a C-channel tensor (+ slack so that tile over-reads past the last row stay in bounds)
+__host__ __device__ inline size_t p4_floats(int C, int H, int W) {
+    return ((size_t)((C + 3) / 4) * p4_plane_px(H, W) + 1024) * 4;
+}
+
+#ifdef __CUDACC__
+// store one 4-channel pixel of group plane `plane` (interior coords y in [0,H), x in [0,W)) and
+// every border position that reflects onto it: row -1 <- row 1, row H <- row H-2, same for columns.
+__device__ __forceinline__ void p4_store(float4* plane, int H, int W, int y, int x, float4 v) {
+    const int Wp = W + 2;
+    float4* p = plane + (size_t)(y + 1) * Wp + (x + 1);
+    *p = v;
+    const bool up = (y == 1), dn = (y == H - 2), lf = (x == 1), rt = (x == W - 2);
+    if (!(up | dn | lf | rt)) return;
+    float4* rows[3] = {p, plane + (x + 1), plane + (size_t)(H + 1) * Wp + (x + 1)};   // self, row -1, row H
+    const bool rowon[3] = {true, up, dn};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (!rowon[a]) continue;
+        if (a) *rows[a] = v;
+        if (lf) rows[a][-(x + 1)] = v;            // column -1
+        if (rt) rows[a][W + 1 - (x + 1)] = v;     // column W
+    }
+}
+#endif
+
 enum ConvEpi {
     EPI_RELU = 0,       // out = relu(conv + bias)
     EPI_NONE = 1,       // out = conv + bias
@@ -15,19 +51,76 @@ enum ConvEpi {
 };
 
 struct ConvArgs {
-    const float* in;    // [Cin][Hin][Win]
-    const float* w;     // packed [Cin][9][CoutPad]
+    const float* in;    // P4 [Cin/4][Hin+2][Win+2][4]
+    const float* w;     // packed weights (layout depends on the kernel)
     const float* bias;  // [CoutPad]
-    const float* res;   // coupling operand (may alias out for EPI_ADD / EPI_SUB)
-    float* out;
+    const float* res;   // coupling operand, P4 (may alias out for EPI_ADD / EPI_SUB)
+    float* out;         // P4
     int Cin, Cout, CoutPad, Hin, Win, Hout, Wout;
     int epi;
 };
+
+#ifdef __CUDACC__
+// Fused epilogue shared by the FFMA and tcgen05 kernels, in two halves so that callers can issue
+// the residual loads of many units before they consume any (memory-level parallelism):
+//   conv_epi_res   — the coupling operand for output channels 4g..4g+3 at output pixel (y, x)
+//   conv_epi_store — combine `v` (= conv + bias) with it and store (+ reflection border)
+__device__ __forceinline__ float4 conv_epi_res(const ConvArgs& a, int g, int y, int x) {
+    const float4* resp = reinterpret_cast<const float4*>(a.res);
+    if (a.epi == EPI_ADD_SQZ) {   // res is the un-squeezed tensor [Cout/16][2Hout+2][2Wout+2][4]
+        const int gq = a.Cout >> 4, k = g / gq, gs = g - k * gq;
+        const int Hh = 2 * a.Hout, Wh = 2 * a.Wout;
+        return resp[(size_t)gs * p4_plane_px(Hh, Wh) + (size_t)(2 * y + (k >> 1) + 1) * (Wh + 2) + (2 * x + (k & 1) + 1)];
+    }
+    return resp[(size_t)g * p4_plane_px(a.Hout, a.Wout) + (size_t)(y + 1) * (a.Wout + 2) + (x + 1)];
+}
+__device__ __forceinline__ void conv_epi_store(const ConvArgs& a, int g, int y, int x, float4 v, float4 r) {
+    float4* outp = reinterpret_cast<float4*>(a.out);
+    switch (a.epi) {
+        case EPI_RELU:
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            break;
+        case EPI_NONE: break;
+        case EPI_ADD:
+        case EPI_ADD_SQZ:
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            break;
+        case EPI_SUB:
+            v.x = r.x - v.x; v.y = r.y - v.y; v.z = r.z - v.z; v.w = r.w - v.w;
+            break;
+        case EPI_SUB_UNSQZ: { // out is the un-squeezed tensor; res is at the conv's own resolution
+            const int gq = a.Cout >> 4, k = g / gq, gs = g - k * gq;
+            const int Hh = 2 * a.Hout, Wh = 2 * a.Wout;
+            v.x = r.x - v.x; v.y = r.y - v.y; v.z = r.z - v.z; v.w = r.w - v.w;
+            p4_store(outp + (size_t)gs * p4_plane_px(Hh, Wh), Hh, Wh, 2 * y + (k >> 1), 2 * x + (k & 1), v);
+            return;
+        }
+    }
+    p4_store(outp + (size_t)g * p4_plane_px(a.Hout, a.Wout), a.Hout, a.Wout, y, x, v);
+}
+__device__ __forceinline__ void conv_epilogue(const ConvArgs& a, int g, int y, int x, float4 v) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.epi >= EPI_ADD) r = conv_epi_res(a, g, y, x);
+    conv_epi_store(a, g, y, x, v, r);
+}
+#endif
 
 int conv_cout_pad(int Cout);
 int launch_pack_conv_weights(const float* w, const float* b, float* wp, float* bp, int Cin, int Cout, int CoutPad,
                              cudaStream_t st);
 int launch_conv3x3_ffma(const ConvArgs& a, int stride, cudaStream_t st);
+
+// fused reversible block for the full-resolution stage (16 -> 4 -> 4 -> 16 channels), block16.cu:
+//   out = res +/- conv3(relu(conv2(relu(conv1(x)))))      weights in the conv3x3_ffma pack layout
+struct Block16Args {
+    const float* x;      // P4 [4 groups][H+2][W+2][4]   (the half-state F is evaluated on)
+    const float* res;    // P4, coupling operand (may alias out)
+    float* out;          // P4
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    int H, W;
+    int sub;             // 0: out = res + F(x)   1: out = res - F(x)
+};
+int launch_rev_block16(const Block16Args& a, cudaStream_t st);
 
 // tensor-core (tcgen05) path, conv_tc.cu
 bool tc_eligible(int Cin, int Cout, int stride);
@@ -36,6 +129,9 @@ size_t tc_packed_floats(int Cin, int Cout, int N, int terms);
 int launch_pack_tc_weights(const float* w, float* wp, int Cin, int Cout, int N, int terms, cudaStream_t st);
 int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st);
 
+// layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
+int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st);   // NCHW -> P4
+int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st);           // P4 -> NCHW
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st);
 int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Win, cudaStream_t st);
 int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st);

@@ -1,0 +1,194 @@
+// layout.cu — the pure data-movement steps of the reversible network, on P4 tensors (kernels.cuh):
+// injective_pad (RevResNet.py:19-31), squeeze / unsqueeze (:34-43), the channel_reduction spread
+// loops fused with split / merge (:8-16, :140-152), and the frame format conversion of the video
+// entry point.  Every kernel that writes a P4 tensor also writes its reflection border (p4_store).
+#include "kernels.cuh"
+
+namespace vst {
+
+static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 16); }
+
+// ------------------------------------------------------------------------------------------
+// injective_pad.forward + split (RevResNet.py:24-28, :8-12): x NCHW [Cimg][H][W] -> s0 P4 with C0
+// channels, channels >= Cimg zero.        injective_pad.inverse (:30-31): first Cimg channels of s0.
+// ------------------------------------------------------------------------------------------
+__global__ void image_to_state_kernel(const float* __restrict__ x, float4* __restrict__ s0, int Cimg, int G, int H,
+                                      int W) {
+    const size_t n = (size_t)H * W, total = (size_t)G * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / n);
+        const size_t p = i - (size_t)g * n;
+        const int y = (int)(p / W), xx = (int)(p - (size_t)y * W);
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = (4 * g + e < Cimg) ? __ldg(x + (size_t)(4 * g + e) * n + p) : 0.f;
+        p4_store(s0 + (size_t)g * p4_plane_px(H, W), H, W, y, xx, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+__global__ void state_to_image_kernel(const float4* __restrict__ s0, float* __restrict__ x, int Cimg, int H, int W) {
+    const size_t n = (size_t)H * W, total = (size_t)((Cimg + 3) / 4) * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / n);
+        const size_t p = i - (size_t)g * n;
+        const int y = (int)(p / W), xx = (int)(p - (size_t)y * W);
+        const float4 v = __ldg(s0 + (size_t)g * p4_plane_px(H, W) + (size_t)(y + 1) * (W + 2) + xx + 1);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (4 * g + k < Cimg) x[(size_t)(4 * g + k) * n + p] = e[k];
+    }
+}
+
+int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st) {
+    const size_t total = (size_t)(C0 / 4) * H * W;
+    ProfScope prof(st, "image_to_state", 0.0, 4.0 * Cimg * H * W + 16.0 * total);
+    image_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(x, reinterpret_cast<float4*>(s0), Cimg, C0 / 4, H, W);
+    return check_launch("image_to_state");
+}
+int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st) {
+    const size_t total = (size_t)((Cimg + 3) / 4) * H * W;
+    ProfScope prof(st, "state_to_image", 0.0, 16.0 * total + 4.0 * Cimg * H * W);
+    state_to_image_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float4*>(s0), x, Cimg, H, W);
+    return check_launch("state_to_image");
+}
+
+// ------------------------------------------------------------------------------------------
+// space <-> depth  (RevResNet.py:34-43)   out[(dy*2+dx)*C + c][h][w] = in[c][2h+dy][2w+dx]
+// With C % 4 == 0 a 4-channel group moves as one 16-byte unit: out group k*(C/4)+g <- in group g.
+// ------------------------------------------------------------------------------------------
+__global__ void space_to_depth_kernel(const float4* __restrict__ in, float4* __restrict__ out, int G, int Ho, int Wo) {
+    const size_t n = (size_t)Ho * Wo, total = (size_t)4 * G * n;
+    const int Hi = 2 * Ho, Wi = 2 * Wo;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int go = (int)(i / n);
+        const size_t p = i - (size_t)go * n;
+        const int h = (int)(p / Wo), w = (int)(p - (size_t)h * Wo);
+        const int k = go / G, g = go - k * G;
+        const float4 v = __ldg(in + (size_t)g * p4_plane_px(Hi, Wi) + (size_t)(2 * h + (k >> 1) + 1) * (Wi + 2) + 2 * w + (k & 1) + 1);
+        p4_store(out + (size_t)go * p4_plane_px(Ho, Wo), Ho, Wo, h, w, v);
+    }
+}
+__global__ void depth_to_space_kernel(const float4* __restrict__ in, float4* __restrict__ out, int G, int Hi, int Wi) {
+    // in [4G groups][Hi][Wi] -> out [G groups][2Hi][2Wi]; iterate over the output
+    const int Ho = 2 * Hi, Wo = 2 * Wi;
+    const size_t n = (size_t)Ho * Wo, total = (size_t)G * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / n);
+        const size_t p = i - (size_t)g * n;
+        const int Y = (int)(p / Wo), X = (int)(p - (size_t)Y * Wo);
+        const int k = (Y & 1) * 2 + (X & 1);
+        const float4 v = __ldg(in + (size_t)(k * G + g) * p4_plane_px(Hi, Wi) + (size_t)((Y >> 1) + 1) * (Wi + 2) + (X >> 1) + 1);
+        p4_store(out + (size_t)g * p4_plane_px(Ho, Wo), Ho, Wo, Y, X, v);
+    }
+}
+
+int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st) {
+    VST_REQUIRE(C % 4 == 0, "space_to_depth: C must be a multiple of 4");
+    const size_t total = (size_t)C * Hin * Win / 4;
+    ProfScope prof(st, "space_to_depth", 0.0, 32.0 * total);
+    space_to_depth_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                                                         C / 4, Hin / 2, Win / 2);
+    return check_launch("space_to_depth");
+}
+int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Win, cudaStream_t st) {
+    VST_REQUIRE(Cout % 4 == 0, "depth_to_space: C must be a multiple of 4");
+    const size_t total = (size_t)Cout * Hin * Win;
+    ProfScope prof(st, "depth_to_space", 0.0, 32.0 * total);
+    depth_to_space_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                                                         Cout / 4, Hin, Win);
+    return check_launch("depth_to_space");
+}
+
+// ------------------------------------------------------------------------------------------
+// latent spread / gather  (RevResNet.py:140-144, :149-152): merge(x1,x2) followed by sp_steps
+// depth-to-space levels, in one pass, converting between the network's P4 state and the NCHW
+// latent the cWCT API exchanges:   z NCHW [Cz][h<<L][w<<L]  <->  x1,x2 P4 [Ch][h][w]
+// One thread moves one 4-channel unit of the state; through every level the four channels stay
+// together (Cz % 4 == 0), landing in latent channels c..c+3 at one pixel.
+// ------------------------------------------------------------------------------------------
+template <bool TO_LATENT>
+__global__ void latent_spread_kernel(float4* __restrict__ x1, float4* __restrict__ x2, float* __restrict__ z, int Ch,
+                                     int h, int w, int L) {
+    const int Gh = Ch / 4;
+    const size_t n = (size_t)h * w, total = (size_t)2 * Gh * n;
+    const int H = h << L, W = w << L;
+    const size_t zplane = (size_t)H * W;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int gg = (int)(i / n);                       // group of merge(x1, x2)
+        const size_t p = i - (size_t)gg * n;
+        const int y = (int)(p / w), x = (int)(p - (size_t)y * w);
+        // walk the levels from the state down to the latent: channel cc = k*D + c', pixel (2y+dy, 2x+dx)
+        int cc = 4 * gg, D = 2 * Ch, Y = y, X = x;
+        for (int l = 0; l < L; ++l) {
+            D >>= 2;
+            const int k = cc / D;
+            cc -= k * D;
+            Y = 2 * Y + (k >> 1);
+            X = 2 * X + (k & 1);
+        }
+        float4* sp = (gg < Gh ? x1 + (size_t)gg * p4_plane_px(h, w) : x2 + (size_t)(gg - Gh) * p4_plane_px(h, w));
+        float* zp = z + (size_t)cc * zplane + (size_t)Y * W + X;
+        if (TO_LATENT) {
+            const float4 v = sp[(size_t)(y + 1) * (w + 2) + x + 1];
+            zp[0] = v.x; zp[zplane] = v.y; zp[2 * zplane] = v.z; zp[3 * zplane] = v.w;
+        } else {
+            p4_store(sp, h, w, y, x, make_float4(__ldg(zp), __ldg(zp + zplane), __ldg(zp + 2 * zplane), __ldg(zp + 3 * zplane)));
+        }
+    }
+}
+
+int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st) {
+    const size_t total = (size_t)2 * Ch * h * w / 4;
+    ProfScope prof(st, "latent_spread", 0.0, 32.0 * total);
+    latent_spread_kernel<true><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<float4*>(const_cast<float*>(x1)),
+                                                              reinterpret_cast<float4*>(const_cast<float*>(x2)), z, Ch, h, w, L);
+    return check_launch("latent_spread");
+}
+int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, cudaStream_t st) {
+    const size_t total = (size_t)2 * Ch * h * w / 4;
+    ProfScope prof(st, "latent_gather", 0.0, 32.0 * total);
+    latent_spread_kernel<false><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<float4*>(x1), reinterpret_cast<float4*>(x2),
+                                                               const_cast<float*>(z), Ch, h, w, L);
+    return check_launch("latent_gather");
+}
+
+// ------------------------------------------------------------------------------------------
+// frame format conversion (video_transfer.py:188, :211-214)
+// ------------------------------------------------------------------------------------------
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ hwc, float* __restrict__ chw, int n, int bgr) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int sc = bgr ? 2 - c : c;
+            chw[(size_t)c * n + i] = (float)hwc[(size_t)i * 3 + sc] / 255.f;   // ToTensor: byte / 255
+        }
+    }
+}
+__global__ void f32_to_u8_kernel(const float* __restrict__ chw, uint8_t* __restrict__ hwc, int n, int bgr) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int dc = bgr ? 2 - c : c;
+            float v = chw[(size_t)c * n + i] * 255.f;
+            v = fminf(fmaxf(v, 0.f), 255.f);                                 // mul(255).clamp(0,255)
+            hwc[(size_t)i * 3 + dc] = (uint8_t)v;                             // .byte() truncates
+        }
+    }
+}
+
+}  // namespace vst
+
+extern "C" int vst_frame_u8_to_f32(const uint8_t* hwc, float* chw, int H, int W, int bgr, void* stream) {
+    using namespace vst;
+    VST_REQUIRE(hwc && chw && H > 0 && W > 0, "vst_frame_u8_to_f32: bad arguments");
+    int n = H * W;
+    u8_to_f32_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(hwc, chw, n, bgr);
+    return check_launch("u8_to_f32");
+}
+extern "C" int vst_frame_f32_to_u8(const float* chw, uint8_t* hwc, int H, int W, int bgr, void* stream) {
+    using namespace vst;
+    VST_REQUIRE(hwc && chw && H > 0 && W > 0, "vst_frame_f32_to_u8: bad arguments");
+    int n = H * W;
+    f32_to_u8_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(chw, hwc, n, bgr);
+    return check_launch("f32_to_u8");
+}

@@ -2,7 +2,7 @@
 //
 // Replaces models/RevResNet.py:166-239 (RevResNet), :68-116 (residual_block), :119-163
 // (channel_reduction).  The plan holds no device memory; every buffer is carved out of the
-// caller's workspace.  State convention: the two half-states (s0,s1) live in two of three
+// caller's workspace, in the P4 layout (kernels.cuh).  State convention: the two half-states (s0,s1) live in two of three
 // rotating planar buffers; an additive-coupling block updates one half IN PLACE
 //     forward : s0 <- s0 + F(s1) ; swap       (RevResNet.py:96-104)
 //     inverse : s1 <- s1 - F(s0) ; swap       (RevResNet.py:106-116)
@@ -71,9 +71,15 @@ struct Workspace {
 };
 
 static size_t half_state_floats(const vst_revnet* n, int H, int W) {
-    size_t a = (size_t)n->c0 * H * W;
-    size_t b = (size_t)n->cr_channel * (H / n->down) * (W / n->down);
-    return align_up(std::max(a, b), 64);
+    // largest half-state over all stages, in the P4 layout (border + slack included)
+    size_t m = p4_floats(n->c0, H, W);
+    int h = H, w = W;
+    for (const BlockDesc& b : n->stack) {
+        if (b.stride == 2) { h /= 2; w /= 2; }
+        m = std::max(m, p4_floats(b.channel, h, w));
+    }
+    m = std::max(m, p4_floats(n->cr_channel, h, w));
+    return align_up(m, 64);
 }
 static size_t temp_floats(const vst_revnet* n, int H, int W) {
     // largest bottleneck tensor: (channel/mult) x h x w over all blocks
@@ -81,9 +87,9 @@ static size_t temp_floats(const vst_revnet* n, int H, int W) {
     int h = H, w = W;
     for (const BlockDesc& b : n->stack) {
         if (b.stride == 2) { h /= 2; w /= 2; }
-        m = std::max(m, (size_t)(b.channel / n->cfg.mult) * h * w);
+        m = std::max(m, p4_floats(b.channel / n->cfg.mult, h, w));
     }
-    for (const BlockDesc& b : n->cr) m = std::max(m, (size_t)(b.channel / n->cfg.mult) * h * w);
+    for (const BlockDesc& b : n->cr) m = std::max(m, p4_floats(b.channel / n->cfg.mult, h, w));
     return align_up(m, 64);
 }
 
@@ -128,6 +134,17 @@ static int run_conv(const vst_revnet* n, const ConvDesc& c, const float* packed,
 static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, const float* x, int Hin, int Win,
                  const Workspace& ws, const float* res, float* out, int epi, cudaStream_t st) {
     const int Ho = Hin / b.stride, Wo = Win / b.stride;
+    if (b.stride == 1 && b.conv[0].Cin == 16 && b.conv[0].Cout == 4 && b.conv[2].Cout == 16 &&
+        (epi == EPI_ADD || epi == EPI_SUB)) {
+        // full-resolution stage: the whole block in one fused CUDA-core kernel (block16.cu)
+        Block16Args a;
+        a.x = x; a.res = res; a.out = out;
+        a.w1 = packed + b.conv[0].pk_w; a.b1 = packed + b.conv[0].pk_b;
+        a.w2 = packed + b.conv[1].pk_w; a.b2 = packed + b.conv[1].pk_b;
+        a.w3 = packed + b.conv[2].pk_w; a.b3 = packed + b.conv[2].pk_b;
+        a.H = Hin; a.W = Win; a.sub = (epi == EPI_SUB) ? 1 : 0;
+        return launch_rev_block16(a, st);
+    }
     if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, st)) return 1;
     if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, st)) return 1;
     if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, st)) return 1;
@@ -137,13 +154,10 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
 static int forward_one(const vst_revnet* n, const float* packed, const float* x, float* z, int H, int W,
                        const Workspace& ws, cudaStream_t st) {
     float *s0 = ws.P[0], *s1 = ws.P[1], *spare = ws.P[2];
-    const size_t plane = (size_t)H * W;
     // injective_pad + split (RevResNet.py:24-28, :8-12): s0 = [x, 0...], s1 = 0
-    VST_CUDA_OK(cudaMemcpyAsync(s0, x, (size_t)n->cfg.in_channel * plane * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    VST_CUDA_OK(cudaMemsetAsync(s0 + (size_t)n->cfg.in_channel * plane, 0,
-                                (size_t)(n->c0 - n->cfg.in_channel) * plane * sizeof(float), st));
-    VST_CUDA_OK(cudaMemsetAsync(s1, 0, (size_t)n->c0 * plane * sizeof(float), st));
-    count_launch(3);
+    if (launch_image_to_state(x, s0, n->cfg.in_channel, n->c0, H, W, st)) return 1;
+    VST_CUDA_OK(cudaMemsetAsync(s1, 0, p4_floats(n->c0, H, W) * sizeof(float), st));
+    count_launch(1);
 
     int c = n->c0, h = H, w = W;
     for (const BlockDesc& b : n->stack) {
@@ -159,10 +173,11 @@ static int forward_one(const vst_revnet* n, const float* packed, const float* x,
             c *= 4; h /= 2; w /= 2;
         }
     }
-    if (n->cr_channel > c) {   // channel_reduction's injective pad (RevResNet.py:133-134)
-        size_t pl = (size_t)h * w;
-        VST_CUDA_OK(cudaMemsetAsync(s0 + (size_t)c * pl, 0, (size_t)(n->cr_channel - c) * pl * sizeof(float), st));
-        VST_CUDA_OK(cudaMemsetAsync(s1 + (size_t)c * pl, 0, (size_t)(n->cr_channel - c) * pl * sizeof(float), st));
+    if (n->cr_channel > c) {   // channel_reduction's injective pad (RevResNet.py:133-134): zero groups c/4..
+        const size_t off = (size_t)(c / 4) * p4_plane_px(h, w) * 4;
+        const size_t cnt = (size_t)((n->cr_channel - c) / 4) * p4_plane_px(h, w) * 4;
+        VST_CUDA_OK(cudaMemsetAsync(s0 + off, 0, cnt * sizeof(float), st));
+        VST_CUDA_OK(cudaMemsetAsync(s1 + off, 0, cnt * sizeof(float), st));
         count_launch(2);
     }
     for (const BlockDesc& b : n->cr) {
@@ -196,10 +211,8 @@ static int inverse_one(const vst_revnet* n, const float* packed, const float* z,
             c /= 4; h *= 2; w *= 2;
         }
     }
-    // merge + injective_pad.inverse (RevResNet.py:30-31): keep the first in_channel planes of x1
-    VST_CUDA_OK(cudaMemcpyAsync(x, s0, (size_t)n->cfg.in_channel * H * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    count_launch(1);
-    return 0;
+    // merge + injective_pad.inverse (RevResNet.py:30-31): keep the first in_channel channels of x1
+    return launch_state_to_image(s0, x, n->cfg.in_channel, H, W, st);
 }
 
 }  // namespace vst
@@ -218,7 +231,7 @@ extern "C" int vst_revnet_create(const vst_revnet_config* cfg, vst_revnet** out)
     int c = n->c0;
     for (int s = 0; s < cfg->n_stages; ++s) {
         const int ch = cfg->n_channels[s], st = cfg->n_strides[s];
-        bool ok = (st == 1 || st == 2) && cfg->n_blocks[s] >= 1 && ch % cfg->mult == 0 && ch / cfg->mult >= 1 &&
+        bool ok = (st == 1 || st == 2) && cfg->n_blocks[s] >= 1 && ch % (4 * cfg->mult) == 0 &&
                   ((st == 1 && ch == c) || (st == 2 && ch == 4 * c));
         if (!ok) {
             delete n;
@@ -232,7 +245,8 @@ extern "C" int vst_revnet_create(const vst_revnet_config* cfg, vst_revnet** out)
     n->c_last = c;
     n->cr_channel = cfg->hidden_dim;
     for (int i = 0; i < cfg->sp_steps; ++i) n->cr_channel *= 4;
-    if (cfg->in_channel < 1 || cfg->in_channel > n->c0 || n->cr_channel < c || n->cr_channel % cfg->mult != 0 ||
+    if (cfg->in_channel < 1 || cfg->in_channel > n->c0 || n->c0 % 4 != 0 || n->cr_channel < c ||
+        n->cr_channel % (4 * cfg->mult) != 0 || ((2 * n->cr_channel) >> (2 * cfg->sp_steps)) % 4 != 0 ||
         (2 * n->cr_channel) % (1 << (2 * cfg->sp_steps)) != 0) {
         delete n;
         set_error("unsupported in_channel=%d / hidden_dim=%d / sp_steps=%d for last width %d", cfg->in_channel,
