@@ -6,9 +6,9 @@
 //
 // Why not tensor cores: N = 4 output channels is below the tcgen05 minimum and the stage is
 // HBM-bound anyway (13.5 FLOP/B); what matters is that the 4-channel intermediates
-// never touch HBM.  A CTA owns a 28x28 output tile: it stages the 34x34x16 input halo tile in
-// shared memory, computes conv1 on 32x32, conv2 on 30x30, conv3 on 28x28, and reads/writes the
-// coupling operand once.  HBM traffic per block: x read once (+halo), res read once, out written
+// never touch HBM.  A CTA owns a 28x28 output tile: it streams the 34x34x16 input halo tile
+// through shared memory, computes conv1 on 32x32, conv2 on 30x30, conv3 on 28x28, and reads/writes
+// the coupling operand once.  HBM traffic per block: x read once (+halo), res read once, out written
 // once — 3 half-states instead of the 4+ of three separate conv launches.
 //
 // Reflection inside the fused tile: intermediates exist only at in-image positions; after each
@@ -16,9 +16,10 @@
 // mirror (row 1 / H-2), which is exactly what the next ReflectionPad2d(1) would read.
 //
 // Data path: the input halo tile arrives by TMA bulk copies (one 544-byte segment per group and
-// row, straight from the P4 tensor, completion on an mbarrier) and stays 4-channel interleaved in
-// shared memory, as do the two intermediates, so every shared-memory access is a conflict-free
-// 16-byte vector.  Thread mapping: 4 warps; lane = tile column, each warp owns a band of rows and
+// row, straight from the P4 tensor, completion on an mbarrier), one 4-channel group at a time
+// through a 2-slot ring so that loads overlap conv1 and three CTAs fit on an SM; it stays
+// 4-channel interleaved in shared memory, as do the two intermediates, so every shared-memory
+// access is a conflict-free 16-byte vector.  Thread mapping: 4 warps; lane = tile column, each warp owns a band of rows and
 // every thread a vertical strip of that band (a 10-row register window per kx serves the three
 // ky taps), all output channels of a pass in registers.  Weights sit in shared memory in the
 // [cin][tap][cout] layout of conv_direct.cu's pack and are read as warp-uniform float4 broadcasts.
@@ -32,10 +33,11 @@ constexpr int T1 = 32;   // conv1 tile edge (TO + 4) == warp width
 constexpr int T2 = 30;   // conv2 tile edge
 constexpr int XT = 34;   // input tile edge
 constexpr int T2_PITCH = 32;
-constexpr int XS_F4 = 4 * XT * XT;     // input halo tile, [group][row][col] float4 (4 channels per element)
+constexpr int XG_F4 = XT * XT;         // one 4-channel group of the input halo tile, [row][col] float4
 constexpr int T1_F4 = T1 * T1;         // [row][col] float4 (the 4 bottleneck channels)
+constexpr int T2_F4 = T2 * T2_PITCH;
 constexpr int W_FLOATS = 16 * 9 * 4 + 4 + 4 * 9 * 4 + 4 + 4 * 9 * 16 + 16;
-constexpr size_t SMEM = (size_t)(XS_F4 + T1_F4) * 16 + (size_t)W_FLOATS * 4 + 16;
+constexpr size_t SMEM = (size_t)(2 * XG_F4 + T1_F4 + T2_F4) * 16 + (size_t)W_FLOATS * 4 + 16;
 }  // namespace b16
 
 __device__ __forceinline__ uint32_t b16_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -69,63 +71,67 @@ __device__ __forceinline__ void tile_reflect(float4* t, int n, int pitch, int oy
     ACC[2] = fmaf(XV, WV.z, ACC[2]);          \
     ACC[3] = fmaf(XV, WV.w, ACC[3]);
 
-__global__ void __launch_bounds__(128, 2) rev_block16_kernel(Block16Args a) {
+__device__ __forceinline__ void b16_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t ba = b16_smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 24) && !done; ++spin)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(ba), "r"(parity) : "memory");
+    if (!done) __trap();
+}
+
+__global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
     using namespace b16;
     extern __shared__ __align__(16) float4 sm4[];
-    float4* xs = sm4;                     // [4][34][34]  input halo tile; later reused for t2 [30][32]
-    float4* t1 = sm4 + XS_F4;             // [32][32]
-    float* ws = reinterpret_cast<float*>(t1 + T1_F4);
+    float4* xs = sm4;                     // [2 slots][34][34]  ring of input-tile channel groups
+    float4* t1 = sm4 + 2 * XG_F4;         // [32][32]
+    float4* t2 = t1 + T1_F4;              // [30][32]
+    float* ws = reinterpret_cast<float*>(t2 + T2_F4);
     float* w1s = ws;                      // [16][9][4]
     float* b1s = w1s + 16 * 9 * 4;
     float* w2s = b1s + 4;                 // [4][9][4]
     float* b2s = w2s + 4 * 9 * 4;
     float* w3s = b2s + 4;                 // [4][9][16]
     float* b3s = w3s + 4 * 9 * 16;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(b3s + 16);
-    float4* t2 = xs;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b3s + 16);   // [2] one per ring slot
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * TO, y0 = blockIdx.y * TO;
     const int H = a.H, W = a.W, Hp = H + 2, Wp = W + 2;
 
-    // ---- input halo tile (image rows y0-3 .. y0+30 = padded rows y0-2 ..): one TMA bulk copy per
-    //      (group, row) segment, straight from the P4 tensor; completion on an mbarrier.
+    // ---- input halo tile (image rows y0-3 .. y0+30 = padded rows y0-2 ..), one channel group at a
+    //      time through a 2-slot ring: one TMA bulk copy per row segment straight from the P4
+    //      tensor, completion on the slot's mbarrier; group g+2 streams in while g+1 is computed.
     const int shift = x0 < 2 ? 2 - x0 : 0;                 // tile columns left of the padded tensor
     const uint32_t seg_bytes = (uint32_t)(XT - shift) * 16;
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b16_smem_u32(bar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 0) {
+    auto issue_group = [&](int g, int slot) {              // executed by all lanes of warp 0
         if (lane == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b16_smem_u32(bar)),
-                         "r"(seg_bytes * 4 * XT) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b16_smem_u32(&bars[slot])),
+                         "r"(seg_bytes * XT) : "memory");
+        __syncwarp();
         const float4* x4 = reinterpret_cast<const float4*>(a.x);
-        for (int i = lane; i < 4 * XT; i += 32) {
-            const int g = i / XT, iy = i - g * XT;
+        for (int iy = lane; iy < XT; iy += 32) {
             const int py = min(max(y0 - 2 + iy, 0), Hp - 1);
             const float4* src = x4 + ((size_t)g * Hp + py) * Wp + (x0 - 2 + shift);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             b16_smem_u32(xs + (g * XT + iy) * XT + shift)),
-                         "l"(src), "r"(seg_bytes), "r"(b16_smem_u32(bar))
+                             b16_smem_u32(xs + slot * XG_F4 + iy * XT + shift)),
+                         "l"(src), "r"(seg_bytes), "r"(b16_smem_u32(&bars[slot]))
                          : "memory");
         }
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b16_smem_u32(&bars[0])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b16_smem_u32(&bars[1])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    if (warp == 0) { issue_group(0, 0); issue_group(1, 1); }
     // ---- weights (conv_direct.cu pack layout [cin][tap][cout]) while the tile is in flight
     for (int i = tid; i < 16 * 9 * 4; i += 128) { w1s[i] = __ldg(a.w1 + i); w3s[i] = __ldg(a.w3 + i); }
     for (int i = tid; i < 4 * 9 * 4; i += 128) w2s[i] = __ldg(a.w2 + i);
     if (tid < 4) { b1s[tid] = __ldg(a.b1 + tid); b2s[tid] = __ldg(a.b2 + tid); }
     if (tid < 16) b3s[tid] = __ldg(a.b3 + tid);
     __syncthreads();
-    {
-        const uint32_t ba = b16_smem_u32(bar);
-        uint32_t done = 0;
-        for (uint32_t spin = 0; spin < (1u << 24) && !done; ++spin)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(ba), "r"(0u) : "memory");
-        if (!done) __trap();
-    }
 
     // ---- conv1 16 -> 4 on the 32x32 tile: t1(r, c) <-> image (y0-2+r, x0-2+c); warp = 8 rows, lane = col
     {
@@ -136,10 +142,12 @@ __global__ void __launch_bounds__(128, 2) rev_block16_kernel(Block16Args a) {
             for (int c = 0; c < 4; ++c) acc[r][c] = b1s[c];
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-#pragma unroll
+            const int slot = g & 1;
+            b16_wait(&bars[slot], (uint32_t)(g >> 1));
+#pragma unroll 1
             for (int kx = 0; kx < 3; ++kx) {
                 float4 v[10];
-                const float4* ip = xs + (g * XT + warp * 8) * XT + lane + kx;
+                const float4* ip = xs + slot * XG_F4 + (warp * 8) * XT + lane + kx;
 #pragma unroll
                 for (int r = 0; r < 10; ++r) v[r] = ip[r * XT];
 #pragma unroll
@@ -158,6 +166,10 @@ __global__ void __launch_bounds__(128, 2) rev_block16_kernel(Block16Args a) {
                     }
                 }
             }
+            if (g + 2 < 4) {
+                __syncthreads();                       // every warp is done reading this slot
+                if (warp == 0) issue_group(g + 2, slot);
+            }
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r)
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(128, 2) rev_block16_kernel(Block16Args a) {
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = b2s[c];
-#pragma unroll
+#pragma unroll 1
         for (int kx = 0; kx < 3; ++kx) {
             float4 v[10];
 #pragma unroll
@@ -195,7 +207,6 @@ __global__ void __launch_bounds__(128, 2) rev_block16_kernel(Block16Args a) {
                 }
             }
         }
-        // xs is dead (every conv1 read happened before the barriers above): t2 reuses its storage
         if (lane < T2)
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(128, 2) rev_block16_kernel(Block16Args a) {
         for (int r = 0; r < 7; ++r)
 #pragma unroll
             for (int c = 0; c < 8; ++c) acc[r][c] = b3s[half * 8 + c];
-#pragma unroll
+#pragma unroll 1
         for (int kx = 0; kx < 3; ++kx) {
             float4 v[9];
 #pragma unroll

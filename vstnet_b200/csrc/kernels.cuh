@@ -21,23 +21,30 @@ __host__ __device__ inline size_t p4_floats(int C, int H, int W) {
 }
 
 #ifdef __CUDACC__
-// store one 4-channel pixel of group plane `plane` (interior coords y in [0,H), x in [0,W)) and
-// every border position that reflects onto it: row -1 <- row 1, row H <- row H-2, same for columns.
-__device__ __forceinline__ void p4_store(float4* plane, int H, int W, int y, int x, float4 v) {
+// the border positions that mirror interior pixel (y, x): row -1 <- row 1, row H <- row H-2, same for
+// columns (and the corners).  Out of line on purpose: it runs for O(perimeter) pixels only and must
+// not bloat the hot epilogues.
+static __device__ __noinline__ void p4_border_fix(float4* plane, int H, int W, int y, int x, float4 v) {
     const int Wp = W + 2;
-    float4* p = plane + (size_t)(y + 1) * Wp + (x + 1);
-    *p = v;
     const bool up = (y == 1), dn = (y == H - 2), lf = (x == 1), rt = (x == W - 2);
-    if (!(up | dn | lf | rt)) return;
-    float4* rows[3] = {p, plane + (x + 1), plane + (size_t)(H + 1) * Wp + (x + 1)};   // self, row -1, row H
+    float4* rows[3] = {plane + (size_t)(y + 1) * Wp, plane, plane + (size_t)(H + 1) * Wp};   // self, row -1, row H
     const bool rowon[3] = {true, up, dn};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         if (!rowon[a]) continue;
-        if (a) *rows[a] = v;
-        if (lf) rows[a][-(x + 1)] = v;            // column -1
-        if (rt) rows[a][W + 1 - (x + 1)] = v;     // column W
+        if (a) rows[a][x + 1] = v;
+        if (lf) rows[a][0] = v;            // column -1
+        if (rt) rows[a][W + 1] = v;        // column W
     }
+}
+__device__ __forceinline__ bool p4_is_edge(int H, int W, int y, int x) {
+    return (y == 1) | (y == H - 2) | (x == 1) | (x == W - 2);
+}
+// store one 4-channel pixel of group plane `plane` (interior coords y in [0,H), x in [0,W)) and
+// every border position that reflects onto it.
+__device__ __forceinline__ void p4_store(float4* plane, int H, int W, int y, int x, float4 v) {
+    plane[(size_t)(y + 1) * (W + 2) + (x + 1)] = v;
+    if (p4_is_edge(H, W, y, x)) p4_border_fix(plane, H, W, y, x, v);
 }
 #endif
 
@@ -128,6 +135,11 @@ int tc_tile_n(int Cout);
 size_t tc_packed_floats(int Cin, int Cout, int N, int terms);
 int launch_pack_tc_weights(const float* w, float* wp, int Cin, int Cout, int N, int terms, cudaStream_t st);
 int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st);
+
+// kx-folded tensor-core path for the convs without a coupling operand (ReLU / plain epilogue), conv_tcx.cu
+bool tcx_eligible(int Cin, int Cout, int stride);
+int launch_pack_tcx_weights(const float* w, float* wp, int Cin, int Cout, int NC, int terms, cudaStream_t st);
+int launch_conv3x3_tcx(const ConvArgs& a, int terms, cudaStream_t st);
 
 // layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
 int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st);   // NCHW -> P4

@@ -18,6 +18,7 @@ struct ConvDesc {
     size_t raw_w, raw_b;  // float offsets into the flat raw parameter buffer
     size_t pk_w, pk_b;    // float offsets into the packed buffer
     bool tc;              // eligible for the tcgen05 implicit-GEMM kernel
+    bool tcx;             // ... in its kx-folded form (no coupling operand: conv1 / conv2 of a block)
     size_t pk_tc;         // float offset of the tensor-core weight pack (sized for hi+lo terms)
 };
 struct BlockDesc {
@@ -56,6 +57,7 @@ static void add_block(vst_revnet* n, std::vector<BlockDesc>& dst, int channel, i
         c.pk_w = n->packed_floats; n->packed_floats += (size_t)c.Cin * 9 * c.CoutPad;
         c.pk_b = n->packed_floats; n->packed_floats += (size_t)c.CoutPad;
         c.tc = tc_eligible(c.Cin, c.Cout, c.stride);
+        c.tcx = k < 2 && tcx_eligible(c.Cin, c.Cout, c.stride);
         c.pk_tc = n->packed_floats;
         if (c.tc) n->packed_floats += tc_packed_floats(c.Cin, c.Cout, tc_tile_n(c.Cout), 3);
     }
@@ -123,6 +125,10 @@ static int run_conv(const vst_revnet* n, const ConvDesc& c, const float* packed,
                     float* out, const float* res, int epi, cudaStream_t st) {
     ConvArgs a = conv_args(c, packed, in, Hin, Win, out, res, epi);
     const int terms = tc_terms(n->precision);
+    if (terms > 0 && c.tcx && (epi == EPI_RELU || epi == EPI_NONE)) {
+        a.w = packed + c.pk_tc;
+        return launch_conv3x3_tcx(a, terms, st);
+    }
     if (terms > 0 && c.tc) {
         a.w = packed + c.pk_tc;
         return launch_conv3x3_tc(a, terms, st);
@@ -283,9 +289,13 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
                                              c.CoutPad, (cudaStream_t)stream))
                     return 1;
                 const int terms = tc_terms(net->precision);
-                if (terms > 0 && c.tc &&
-                    launch_pack_tc_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, tc_tile_n(c.Cout), terms,
-                                           (cudaStream_t)stream))
+                if (terms > 0 && c.tcx) {
+                    if (launch_pack_tcx_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, c.Cout, terms,
+                                                (cudaStream_t)stream))
+                        return 1;
+                } else if (terms > 0 && c.tc &&
+                           launch_pack_tc_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, tc_tile_n(c.Cout), terms,
+                                                  (cudaStream_t)stream))
                     return 1;
             }
     return 0;

@@ -1,0 +1,57 @@
+"""Host-side pre/post-processing shared by the entry points (PIL / numpy only, no CUDA).
+
+Mirrors the reference's ``utils/utils.py`` behaviour that the stylization path depends on:
+``img_resize`` (:90-101) and ``load_segment`` (:104-153, colour -> label 0..8).  ``load_segment`` is
+vectorised (the reference loops over pixels in Python) but keeps the same colour table and the
+nearest-colour (L1) rule for colours that are not in it.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+from PIL import Image
+
+SEG_COLORS = np.array([  # ref: utils/utils.py:106-116, index = label
+    (0, 0, 0), (255, 255, 255), (0, 255, 0), (0, 0, 255), (255, 0, 0), (255, 255, 0), (128, 128, 128),
+    (0, 255, 255), (255, 0, 255)], dtype=np.int32)
+
+
+def img_resize(img, max_size, down_scale=None):
+    """Cap the long edge at ``max_size`` and floor H, W to multiples of ``down_scale`` (PIL bicubic)."""
+    w, h = img.size
+    if max(w, h) > max_size:
+        w = int(1.0 * img.size[0] / max(img.size) * max_size)
+        h = int(1.0 * img.size[1] / max(img.size) * max_size)
+        img = img.resize((w, h), Image.BICUBIC)
+    if down_scale is not None:
+        w = w // down_scale * down_scale
+        h = h // down_scale * down_scale
+        img = img.resize((w, h), Image.BICUBIC)
+    return img
+
+
+def labels_from_colors(rgb):
+    """uint8 [H,W,3] colour-coded segmentation -> uint8 [H,W] labels (nearest table colour in L1)."""
+    a = np.asarray(rgb, dtype=np.int32)
+    d = np.abs(a[:, :, None, :] - SEG_COLORS[None, None, :, :]).sum(-1)          # [H,W,9]
+    # the reference visits the table in dict order (blue, green, black, white, red, ...) and keeps the first
+    # strict minimum; reproduce that order for ties
+    order = np.array([3, 2, 0, 1, 4, 5, 6, 7, 8])
+    return order[np.argmin(d[:, :, order], axis=-1)].astype(np.uint8)
+
+
+def load_segment(image_path, size=None):
+    """ref: utils/utils.py:104-153.  ``size`` = (w, h) nearest-neighbour resize before labelling."""
+    if not os.path.exists(image_path):
+        print("Can not find image path: %s " % image_path)
+        return None
+    image = Image.open(image_path).convert("RGB")
+    if size is not None:
+        image = image.resize((size[0], size[1]), Image.NEAREST)
+    return labels_from_colors(np.array(image))
+
+
+def to_uint8_hwc(stylized):
+    """fp32 CUDA/CPU [1,3,H,W] -> uint8 numpy [H,W,3]: mul(255).clamp(0,255).byte() (image_transfer.py:218)."""
+    return stylized[0].mul(255).clamp(0, 255).byte().permute(1, 2, 0).cpu().numpy()

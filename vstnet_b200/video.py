@@ -19,6 +19,25 @@ def shard_frames(n_frames, rank, world_size):
     return list(range(rank, n_frames, world_size))
 
 
+def broadcast_style_stats(pre, nbytes_of, device, group=None, src=0):
+    """The path's only collective: ``src`` sends the hoisted style statistics (an opaque byte buffer per
+    sample, 8.6 KB for C=32 / one label) to every rank.  ``pre`` is the dict of
+    ``cWCT.precompute_style`` on ``src`` and ``None`` elsewhere; ``nbytes_of(C, L)`` sizes one buffer.
+    Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    meta = torch.zeros(4, dtype=torch.int64, device=device)
+    if rank == src:
+        meta[:] = torch.tensor([pre["L"], int(pre["masked"]), pre["C"], len(pre["stats"])])
+    dist.broadcast(meta, src=src, group=group)
+    L, masked, C_, B = (int(v) for v in meta.tolist())
+    nbytes = nbytes_of(C_, L)
+    stats = pre["stats"] if rank == src else [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(B)]
+    for s in stats:
+        dist.broadcast(s, src=src, group=group)
+    return {"stats": stats, "L": L, "masked": bool(masked), "C": C_}
+
+
 class VideoStylizer:
     def __init__(self, net: RevResNet, cwct: cWCT | None = None, alpha_c=None):
         self.net = net
@@ -42,16 +61,8 @@ class VideoStylizer:
             zs = self.net(style.to(dev), forward=True)
             pre = self.cwct.precompute_style(zs, style_seg)
         if distributed:
-            meta = torch.zeros(4, dtype=torch.int64, device=dev)
-            if rank == src:
-                meta[:] = torch.tensor([pre["L"], int(pre["masked"]), pre["C"], len(pre["stats"])])
-            dist.broadcast(meta, src=src, group=group)
-            L, masked, C_, B = (int(v) for v in meta.tolist())
-            nbytes = int(self._lib.vst_cwct_stats_bytes(C_, L))
-            stats = pre["stats"] if rank == src else [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(B)]
-            for s in stats:
-                dist.broadcast(s, src=src, group=group)       # the path's only data collective
-            pre = {"stats": stats, "L": L, "masked": bool(masked), "C": C_}
+            nbytes_of = lambda C_, L: int(self._lib.vst_cwct_stats_bytes(C_, L))
+            pre = broadcast_style_stats(pre if rank == src else None, nbytes_of, dev, group, src)
         self.style_pre = pre
         return pre
 
