@@ -265,15 +265,19 @@ def run_ours(args):
             traffic = json.load(open(tf)).get(top_name)
         except Exception:
             traffic = None
-    if ai > pk["bf16_tflops_sustained"] * 1e3 / pk["hbm_gbs"] / 4:      # above the TF32 ridge -> tensor bound
+    # kind::tf32 runs at half the bf16 rate, so the tensor roof of these kernels is the measured bf16 figure / 2;
+    # `achieved` counts USEFUL conv flops (one term), not the 2x / 3x issued by the split-precision modes.
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    if ai > tf32_peak * 1e3 / pk["hbm_gbs"]:                            # above the TF32 ridge -> tensor bound
         ach = top["flops"] / top["ms"] / 1e9
-        roof = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
-                "peak_source": pk["source"] + " bf16 dense sustained (tf32 peak is half of it)"}
+        roof = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": tf32_peak,
+                "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
+                "peak_source": pk["source"] + " bf16 dense sustained / 2 (tf32 rate); achieved = useful 1-term flops, "
+                               "%s issues %dx" % (args.precision, {"tf32": 1, "tf32x2": 2, "tf32x3": 3}.get(args.precision, 1))}
     else:
         ach = top["bytes"] / top["ms"] / 1e6
         roof = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"]}
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"] + " copy bandwidth"}
     roof["launches"] = top["launches"]
     roof["ms_per_launch"] = top["ms"] / max(1, top["launches"])
 
@@ -311,7 +315,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32")
+    ap.add_argument("--precision", default="tf32x2", help="conv arithmetic: tf32x2 (default, meets both tolerances) | tf32x3 | tf32 | fp32")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

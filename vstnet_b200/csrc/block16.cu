@@ -37,7 +37,7 @@ constexpr int XG_F4 = XT * XT;         // one 4-channel group of the input halo 
 constexpr int T1_F4 = T1 * T1;         // [row][col] float4 (the 4 bottleneck channels)
 constexpr int T2_F4 = T2 * T2_PITCH;
 constexpr int W_FLOATS = 16 * 9 * 4 + 4 + 4 * 9 * 4 + 4 + 4 * 9 * 16 + 16;
-constexpr size_t SMEM = (size_t)(2 * XG_F4 + T1_F4 + T2_F4) * 16 + (size_t)W_FLOATS * 4 + 16;
+constexpr size_t SMEM = (size_t)(2 * XG_F4 + T1_F4 + T2_F4) * 16 + (size_t)W_FLOATS * 4 + 32;
 }  // namespace b16
 
 __device__ __forceinline__ uint32_t b16_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,6 +45,8 @@ __device__ __forceinline__ uint32_t b16_smem_u32(const void* p) { return (uint32
 // overwrite the tile rows/cols that stand for image row/col -1 and H/W with their mirrors.
 // tile(r, c) <-> image(oy + r, ox + c); square tile of edge n, row pitch `pitch` (float4 elements).
 __device__ __forceinline__ void tile_reflect(float4* t, int n, int pitch, int oy, int ox, int H, int W, int tid) {
+    // CTA-uniform early out: interior tiles hold no out-of-image positions
+    if (oy >= 0 && ox >= 0 && oy + n <= H && ox + n <= W) return;
     {
         const int rm = -1 - oy, rs = 1 - oy;            // row -1 <- row 1
         if (rm >= 0 && rs < n)
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
     float* b2s = w2s + 4 * 9 * 4;
     float* w3s = b2s + 4;                 // [4][9][16]
     float* b3s = w3s + 4 * 9 * 16;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b3s + 16);   // [2] one per ring slot
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b3s + 16);   // [3] one per ring slot + weights
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int x0 = blockIdx.x * TO, y0 = blockIdx.y * TO;
@@ -122,20 +124,25 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b16_smem_u32(&bars[0])), "r"(1));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b16_smem_u32(&bars[1])), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b16_smem_u32(&bars[2])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (warp == 0) { issue_group(0, 0); issue_group(1, 1); }
-    // ---- weights (conv_direct.cu pack layout [cin][tap][cout]) while the tile is in flight
-    for (int i = tid; i < 16 * 9 * 4; i += 128) { w1s[i] = __ldg(a.w1 + i); w3s[i] = __ldg(a.w3 + i); }
-    for (int i = tid; i < 4 * 9 * 4; i += 128) w2s[i] = __ldg(a.w2 + i);
-    if (tid < 4) { b1s[tid] = __ldg(a.b1 + tid); b2s[tid] = __ldg(a.b2 + tid); }
-    if (tid < 16) b3s[tid] = __ldg(a.b3 + tid);
-    __syncthreads();
-
+    if (warp == 0) {
+        if (lane == 0) {   // weights: the block's three packs are one contiguous 5280-byte run (w1 b1 w2 b2 w3 b3)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b16_smem_u32(&bars[2])),
+                         "r"((uint32_t)(W_FLOATS * 4)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             b16_smem_u32(ws)), "l"(a.w1), "r"((uint32_t)(W_FLOATS * 4)), "r"(b16_smem_u32(&bars[2]))
+                         : "memory");
+        }
+        issue_group(0, 0);
+        issue_group(1, 1);
+    }
     // ---- conv1 16 -> 4 on the 32x32 tile: t1(r, c) <-> image (y0-2+r, x0-2+c); warp = 8 rows, lane = col
     {
         float acc[8][4];
+        b16_wait(&bars[2], 0);                 // weights landed
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -287,6 +294,9 @@ int launch_rev_block16(const Block16Args& a, cudaStream_t st) {
         attr_set = true;
     }
     VST_REQUIRE(a.H >= 4 && a.W >= 4, "rev_block16: image too small (%dx%d)", a.H, a.W);
+    VST_REQUIRE(a.b1 == a.w1 + 576 && a.w2 == a.b1 + 4 && a.b2 == a.w2 + 144 && a.w3 == a.b2 + 4 && a.b3 == a.w3 + 576 &&
+                    ((uintptr_t)a.w1 & 15) == 0,
+                "rev_block16: the block's weight packs must be one contiguous 16-byte aligned run");
     dim3 grid(cdiv(a.W, b16::TO), cdiv(a.H, b16::TO));
     const double px = (double)a.H * a.W;
     ProfScope prof(st, "rev_block16 (16>4>4>16)", 2.0 * 9 * (16 * 4 + 4 * 4 + 4 * 16) * px, 3.0 * 64.0 * px);

@@ -386,9 +386,12 @@ static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
     return check_launch("conv3x3_tc");
 }
 
-static int tc_wide_n() {   // experiment knob: VST_TC_WIDE=128 -> N=128, R=2 tiles where Cout % 128 == 0
+// cout tile width: 128 (R = 2 rows) where Cout allows — a K=8 UMMA costs the same ~66 cycles for N = 64 and
+// N = 128 (it is bound by fetching A), so wider tiles halve the tensor time of the 64>256 coupling convs —
+// else 64 (R = 4) or 16.  VST_TC_WIDE=0 forces the narrow tiles (developer knob).
+static int tc_wide_n() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("VST_TC_WIDE"); v = e ? atoi(e) : 0; }
+    if (v < 0) { const char* e = getenv("VST_TC_WIDE"); v = e ? atoi(e) : 128; }
     return v;
 }
 int tc_tile_n(int Cout) {
@@ -406,7 +409,11 @@ int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st) {
     VST_REQUIRE(a.Hin >= 2 && a.Win >= 2, "conv3x3: reflection pad needs H,W >= 2");
     VST_REQUIRE(a.Hin == a.Hout && a.Win == a.Wout, "conv3x3_tc is stride 1");
     const int N = tc_tile_n(a.Cout);
-    if (N == 128) return launch_tc_cfg<128, 2, 2>(a, st);
+    if (N == 128) {
+        if (terms == 1) return launch_tc_cfg<128, 2, 1>(a, st);
+        if (terms == 2) return launch_tc_cfg<128, 2, 2>(a, st);
+        return launch_tc_cfg<128, 2, 3>(a, st);
+    }
     if (N == 64) {
         if (terms == 1) return launch_tc_cfg<64, 4, 1>(a, st);
         if (terms == 2) return launch_tc_cfg<64, 4, 2>(a, st);

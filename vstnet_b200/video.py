@@ -93,13 +93,13 @@ class VideoStylizer:
         st = torch.cuda.current_stream(dev)
         if frame.dtype == torch.uint8:
             H, W = frame.shape[0], frame.shape[1]
-            u8 = frame.to(dev, non_blocking=True)
+            u8 = frame.contiguous().to(dev, non_blocking=True)
             x = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
             _lib.check(self._lib.vst_frame_u8_to_f32(u8.data_ptr(), x.data_ptr(), H, W, int(bgr), st.cuda_stream),
                        "vst_frame_u8_to_f32")
         else:
             H, W = frame.shape[2], frame.shape[3]
-            x = frame.to(dev, non_blocking=True)
+            x = frame.contiguous().to(dev, non_blocking=True)
         y = self.stylize(x, content_seg)
         o = torch.empty(H, W, 3, dtype=torch.uint8, device=dev)
         _lib.check(self._lib.vst_frame_f32_to_u8(y.data_ptr(), o.data_ptr(), H, W, int(bgr), st.cuda_stream),
