@@ -23,4 +23,4 @@ t0 = a[a > 0].min()
 print("shape", shape, "rc", rc)
 for r in range(8):
     v = a[r][a[r] > 0] - t0
-    print("%-15s n=%4d : %s" % (names[r], len(v), " ".join("%7d" % q for q in v[:(36 if r == 7 else 20)])))
+    print("%-15s n=%4d : %s" % (names[r], len(v), " ".join("%7d" % q for q in v[:(40 if r == 7 else 20)])))

@@ -349,6 +349,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
 
 static long long* g_tc_trace = nullptr;
 
+// developer aid: VST_TC_TRACE="cin,cout" hands a zeroed stamp buffer to launches of that shape
+long long* tc_trace_buffer(int Cin, int Cout, cudaStream_t st) {
+    static int tr_cin = -1, tr_cout = -1;
+    if (tr_cin < 0) {
+        const char* e = getenv("VST_TC_TRACE");
+        tr_cin = 0;
+        if (e) sscanf(e, "%d,%d", &tr_cin, &tr_cout);
+    }
+    if (tr_cin != Cin || tr_cout != Cout) return nullptr;
+    static long long* buf = nullptr;
+    if (!buf) cudaMalloc(&buf, 8 * 4096 * sizeof(long long));
+    cudaMemsetAsync(buf, 0, 8 * 4096 * sizeof(long long), st);
+    g_tc_trace = buf;
+    return buf;
+}
+
 template <int N, int R, int TERMS>
 static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
     using Cfg = TcCfg<N, R, TERMS>;
@@ -361,20 +377,7 @@ static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
     TcTiles tl;
     tl.n_xt = cdiv(a.Wout, 128); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / N;
     tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;
-    tl.trace = nullptr;
-    static int tr_cin = -1, tr_cout = -1;
-    if (tr_cin < 0) {
-        const char* e = getenv("VST_TC_TRACE");
-        tr_cin = 0;
-        if (e) sscanf(e, "%d,%d", &tr_cin, &tr_cout);
-    }
-    if (tr_cin == a.Cin && tr_cout == a.Cout && a.epi <= EPI_SUB) {
-        static long long* buf = nullptr;
-        if (!buf) { cudaMalloc(&buf, 8 * 4096 * sizeof(long long)); }
-        cudaMemsetAsync(buf, 0, 8 * 4096 * sizeof(long long), st);
-        tl.trace = buf;
-        g_tc_trace = buf;
-    }
+    tl.trace = (a.epi <= EPI_SUB) ? tc_trace_buffer(a.Cin, a.Cout, st) : nullptr;
     const int grid = std::min(tl.n_tiles, num_sms());
     char cls[40];
     snprintf(cls, sizeof(cls), "conv3x3_tc%d %d>%d", TERMS, a.Cin, a.Cout);

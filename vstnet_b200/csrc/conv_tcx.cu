@@ -81,7 +81,9 @@ int launch_pack_tcx_weights(const float* w, float* wp, int Cin, int Cout, int NC
 
 struct TcxTiles {
     int n_xt, n_yt, n_ct, n_tiles;
+    long long* trace;   // developer aid (VST_TC_TRACE): CTA 0 stamps clock64() per role event, 4096 slots per role
 };
+#define TCX_TRACE(role, idx) do { if (tl.trace && blockIdx.x == 0 && (idx) < 4096) tl.trace[(role) * 4096 + (idx)] = clock64(); } while (0)
 
 constexpr int TCX_THREADS = 448;   // 8 epilogue + 4 converter warps, operand producer, UMMA issuer
 
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
                 for (int c = 0; c < n_chunks; ++c, ++it) {
                     const int s = it % NS;
                     mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
+                    TCX_TRACE(0, it);
                     uint8_t* A = stage_base + (size_t)s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&loaded[s], Cfg::A_TERM_BYTES + Cfg::B_BYTES);
 #pragma unroll
@@ -154,11 +157,13 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
                 const uint32_t b = tcount % NACC;
                 mbar_wait(&acc_empty[b], ((tcount / NACC) & 1) ^ 1);
                 tc_fence_after();
+                TCX_TRACE(5, tcount);
                 const uint32_t acc = tmem_base + b * Cfg::ACC_COLS;
                 for (int c = 0; c < n_chunks; ++c, ++it) {
                     const int s = it % NS;
                     mbar_wait(&ready[s], (it / NS) & 1);
                     tc_fence_after();
+                    TCX_TRACE(3, it);
                     const uint32_t Aaddr = smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
                     const uint32_t Baddr = Aaddr + Cfg::A_BYTES;
 #pragma unroll
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
                         }
                     }
                     umma_commit(&empty[s]);
+                    TCX_TRACE(4, it);
                 }
                 umma_commit(&acc_full[b]);
             }
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
             for (int c = 0; c < n_chunks; ++c, ++it) {
                 const int s = it % NS;
                 mbar_wait(&loaded[s], (it / NS) & 1);
+                if (ctid == 0) TCX_TRACE(1, it);
                 float4* hi = reinterpret_cast<float4*>(stage_base + (size_t)s * Cfg::STAGE_BYTES);
                 float4* lo = reinterpret_cast<float4*>(stage_base + (size_t)s * Cfg::STAGE_BYTES + Cfg::A_TERM_BYTES);
 #pragma unroll 4
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
                 }
                 fence_proxy_async();
                 mbar_arrive(&ready[s]);
+                if (ctid == 0) TCX_TRACE(2, it);
             }
         }
     } else {
@@ -226,6 +234,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
             float* ex = exch + (size_t)(tcount & 1) * (R * 4 * 2 * NC);
             mbar_wait(&acc_full[b], (tcount / NACC) & 1);
             tc_fence_after();
+            if (tid == 0) TCX_TRACE(6, tcount);
             // ---- phase 1: publish the partial sums a neighbouring warp needs (lane 31's kx=0, lane 0's kx=2)
 #pragma unroll 1
             for (int r = 0; r < rows; ++r) {
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
                 }
             }
             named_barrier(1, 256);
+            if (tid == 0) TCX_TRACE(7, 2 * tcount);
             // ---- phase 2: out[m] = D[m-1][kx=0] + D[m][kx=1] + D[m+1][kx=2]
             const bool lf = xin && (x == 1), rt = xin && (x == W - 2);
 #pragma unroll 1
@@ -257,17 +267,28 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
                     tmem_ld<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0);
                     tmem_ld<CH>(trow + (uint32_t)(r * NP + 1 * NC + c0), v1);
                     tmem_ld<CH>(trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
+                    if (tid == 0 && tcount == 1) TCX_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 0);
                     const int cb = half * HC + c0;                  // first cout of this chunk (within the tile)
                     const float* exl = ex + ((r * 4 + (q > 0 ? q - 1 : 0)) * 2 + 0) * NC + cb;   // left neighbour warp, lane 31
                     const float* exr = ex + ((r * 4 + (q < 3 ? q + 1 : 3)) * 2 + 1) * NC + cb;   // right neighbour warp, lane 0
+                    // neighbour-warp values: warp-uniform addresses (broadcast loads), selected without branching
+                    float el[CH], er[CH];
+#pragma unroll
+                    for (int i = 0; i < CH; i += 4) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(exl + i);
+                        const float4 b4 = *reinterpret_cast<const float4*>(exr + i);
+                        el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
+                        er[i] = b4.x; er[i + 1] = b4.y; er[i + 2] = b4.z; er[i + 3] = b4.w;
+                    }
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
-                        float l = __shfl_up_sync(0xffffffffu, v0[i], 1);
-                        float rr = __shfl_down_sync(0xffffffffu, v2[i], 1);
-                        if (lane == 0) l = exl[i];
-                        if (lane == 31) rr = exr[i];
+                        const float ls = __shfl_up_sync(0xffffffffu, v0[i], 1);
+                        const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
+                        const float l = (lane == 0) ? el[i] : ls;
+                        const float rr = (lane == 31) ? er[i] : rs;
                         v1[i] = (l + v1[i]) + rr;
                     }
+                    if (tid == 0 && tcount == 1) TCX_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 1);
                     if (xin) {
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) {
@@ -296,10 +317,12 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
                             }
                         }
                     }
+                    if (tid == 0 && tcount == 1) TCX_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 2);
                 }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[b]);
+            if (tid == 0) TCX_TRACE(7, 2 * tcount + 1);
         }
     }
 
@@ -323,6 +346,7 @@ static int launch_tcx_cfg(const ConvArgs& a, cudaStream_t st) {
     TcxTiles tl;
     tl.n_xt = cdiv(a.Wout, Cfg::XS); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / NC;
     tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;
+    tl.trace = tc_trace_buffer(a.Cin, a.Cout, st);
     const int grid = std::min(tl.n_tiles, num_sms());
     char cls[40];
     snprintf(cls, sizeof(cls), "conv3x3_tcx%d %d>%d", TERMS, a.Cin, a.Cout);

@@ -135,6 +135,7 @@ int tc_tile_n(int Cout);
 size_t tc_packed_floats(int Cin, int Cout, int N, int terms);
 int launch_pack_tc_weights(const float* w, float* wp, int Cin, int Cout, int N, int terms, cudaStream_t st);
 int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st);
+long long* tc_trace_buffer(int Cin, int Cout, cudaStream_t st);   // developer aid, conv_tc.cu
 
 // kx-folded tensor-core path for the convs without a coupling operand (ReLU / plain epilogue), conv_tcx.cu
 bool tcx_eligible(int Cin, int Cout, int stride);

@@ -103,21 +103,84 @@ int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Wi
 // latent spread / gather  (RevResNet.py:140-144, :149-152): merge(x1,x2) followed by sp_steps
 // depth-to-space levels, in one pass, converting between the network's P4 state and the NCHW
 // latent the cWCT API exchanges:   z NCHW [Cz][h<<L][w<<L]  <->  x1,x2 P4 [Ch][h][w]
-// One thread moves one 4-channel unit of the state; through every level the four channels stay
-// together (Cz % 4 == 0), landing in latent channels c..c+3 at one pixel.
+// Through every level a 4-channel group stays together (Cz % 4 == 0) and lands in latent channels
+// c..c+3 at one pixel; the 2^L x-neighbours of a latent row come from 2^L different groups of the
+// same state pixel.  A thread therefore moves 2^L groups (16-byte loads, coalesced across the warp),
+// transposes them in registers and writes 2^L-wide vectors per latent channel: both sides coalesced.
 // ------------------------------------------------------------------------------------------
-template <bool TO_LATENT>
+template <int L, bool TO_LATENT>
 __global__ void latent_spread_kernel(float4* __restrict__ x1, float4* __restrict__ x2, float* __restrict__ z, int Ch,
-                                     int h, int w, int L) {
+                                     int h, int w) {
+    constexpr int S = 1 << L;                               // sub-positions per axis
+    const int Gh = Ch / 4, Cz = (2 * Ch) >> (2 * L), Gz = Cz / 4;
+    const int H = h << L, W = w << L;
+    const size_t n = (size_t)h * w, total = (size_t)Gz * S * n, zplane = (size_t)H * W, splane = p4_plane_px(h, w);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w);
+        const int y = (int)((i / w) % h);
+        const int yy = (int)((i / n) % S);                  // sub-row inside the S x S block of this state pixel
+        const int cg = (int)(i / (n * S));                  // latent channel group
+        float4 v[S];
+        float4* src[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {                       // s = sub-column
+            int cc = 4 * cg;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {                   // level l consumes bit (L-1-l) of yy (row) and s (column)
+                const int k = (((yy >> (L - 1 - l)) & 1) << 1) | ((s >> (L - 1 - l)) & 1);
+                cc += k * ((2 * Ch) >> (2 * (l + 1)));
+            }
+            const int gg = cc >> 2;
+            src[s] = (gg < Gh ? x1 + (size_t)gg * splane : x2 + (size_t)(gg - Gh) * splane);
+        }
+        float* zp = z + (size_t)(4 * cg) * zplane + (size_t)((y << L) + yy) * W + ((size_t)x << L);
+        if (TO_LATENT) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) v[s] = src[s][(size_t)(y + 1) * (w + 2) + x + 1];
+            if constexpr (S == 4) {
+                *reinterpret_cast<float4*>(zp) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+                *reinterpret_cast<float4*>(zp + zplane) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+                *reinterpret_cast<float4*>(zp + 2 * zplane) = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+                *reinterpret_cast<float4*>(zp + 3 * zplane) = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+            } else {
+                *reinterpret_cast<float2*>(zp) = make_float2(v[0].x, v[S - 1].x);
+                *reinterpret_cast<float2*>(zp + zplane) = make_float2(v[0].y, v[S - 1].y);
+                *reinterpret_cast<float2*>(zp + 2 * zplane) = make_float2(v[0].z, v[S - 1].z);
+                *reinterpret_cast<float2*>(zp + 3 * zplane) = make_float2(v[0].w, v[S - 1].w);
+            }
+        } else {
+            float r[4][S];
+            if constexpr (S == 4) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(zp + e * zplane));
+                    r[e][0] = t.x; r[e][1] = t.y; r[e][2] = t.z; r[e][3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 t = __ldg(reinterpret_cast<const float2*>(zp + e * zplane));
+                    r[e][0] = t.x; r[e][S - 1] = t.y;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) p4_store(src[s], h, w, y, x, make_float4(r[0][s], r[1][s], r[2][s], r[3][s]));
+        }
+    }
+}
+
+// any other depth (not used by the reference's two modes): one 4-channel unit per thread
+template <bool TO_LATENT>
+__global__ void latent_spread_generic_kernel(float4* __restrict__ x1, float4* __restrict__ x2, float* __restrict__ z,
+                                             int Ch, int h, int w, int L) {
     const int Gh = Ch / 4;
     const size_t n = (size_t)h * w, total = (size_t)2 * Gh * n;
     const int H = h << L, W = w << L;
     const size_t zplane = (size_t)H * W;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int gg = (int)(i / n);                       // group of merge(x1, x2)
+        const int gg = (int)(i / n);
         const size_t p = i - (size_t)gg * n;
         const int y = (int)(p / w), x = (int)(p - (size_t)y * w);
-        // walk the levels from the state down to the latent: channel cc = k*D + c', pixel (2y+dy, 2x+dx)
         int cc = 4 * gg, D = 2 * Ch, Y = y, X = x;
         for (int l = 0; l < L; ++l) {
             D >>= 2;
@@ -137,19 +200,22 @@ __global__ void latent_spread_kernel(float4* __restrict__ x1, float4* __restrict
     }
 }
 
+template <bool TO_LATENT>
+static int launch_spread_any(float* x1, float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st) {
+    const size_t units = (size_t)2 * Ch * h * w / 4;
+    float4 *a = reinterpret_cast<float4*>(x1), *b = reinterpret_cast<float4*>(x2);
+    ProfScope prof(st, TO_LATENT ? "latent_spread" : "latent_gather", 0.0, 32.0 * units);
+    if (L == 2) latent_spread_kernel<2, TO_LATENT><<<ew_grid(units / 4), 256, 0, st>>>(a, b, z, Ch, h, w);
+    else if (L == 1) latent_spread_kernel<1, TO_LATENT><<<ew_grid(units / 2), 256, 0, st>>>(a, b, z, Ch, h, w);
+    else latent_spread_generic_kernel<TO_LATENT><<<ew_grid(units), 256, 0, st>>>(a, b, z, Ch, h, w, L);
+    return check_launch(TO_LATENT ? "latent_spread" : "latent_gather");
+}
+
 int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st) {
-    const size_t total = (size_t)2 * Ch * h * w / 4;
-    ProfScope prof(st, "latent_spread", 0.0, 32.0 * total);
-    latent_spread_kernel<true><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<float4*>(const_cast<float*>(x1)),
-                                                              reinterpret_cast<float4*>(const_cast<float*>(x2)), z, Ch, h, w, L);
-    return check_launch("latent_spread");
+    return launch_spread_any<true>(const_cast<float*>(x1), const_cast<float*>(x2), z, Ch, h, w, L, st);
 }
 int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, cudaStream_t st) {
-    const size_t total = (size_t)2 * Ch * h * w / 4;
-    ProfScope prof(st, "latent_gather", 0.0, 32.0 * total);
-    latent_spread_kernel<false><<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<float4*>(x1), reinterpret_cast<float4*>(x2),
-                                                               const_cast<float*>(z), Ch, h, w, L);
-    return check_launch("latent_gather");
+    return launch_spread_any<false>(x1, x2, const_cast<float*>(z), Ch, h, w, L, st);
 }
 
 // ------------------------------------------------------------------------------------------
