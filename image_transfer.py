@@ -33,12 +33,12 @@ def build_parser():
     p.add_argument('--content_seg', type=str, default=None)
     p.add_argument('--style_seg', type=str, default=None)
     p.add_argument('--auto_seg', action='store_true', default=False)
-    p.add_argument('--precision', type=str, default='tf32x2', help="conv arithmetic: fp32 | tf32x3 | tf32x2 | tf32")
+    p.add_argument('--precision', type=str, default='f16x2', help="conv arithmetic: f16x2 | tf32x2 | tf32x3 | tf32 | fp32")
     p.add_argument('--synthetic', type=str, default=None, help="HxW: random images + random-init weights")
     return p
 
 
-def build_network(mode, precision="tf32x2"):
+def build_network(mode, precision="f16x2"):
     from models.RevResNet import RevResNet
     if mode.lower() == "photorealistic":
         return RevResNet(hidden_dim=16, sp_steps=2, precision=precision)       # ref :45

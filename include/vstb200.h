@@ -74,6 +74,8 @@ typedef struct vst_revnet vst_revnet; /* host-side plan; holds no device memory 
 #define VST_CONV_TF32X3 1   /* tcgen05 kind::tf32, 3-term error-compensated split (fp32-equivalent) */
 #define VST_CONV_TF32X2 2   /* tcgen05 kind::tf32, activations split hi+lo, weights rounded to tf32 */
 #define VST_CONV_TF32 3     /* tcgen05 kind::tf32, single term                              */
+#define VST_CONV_F16X2 4    /* tcgen05 kind::f16 on the non-coupling convs: activations split hi+lo in fp16 (22 bits),
+                               weights rounded to fp16 (11 bits, as tf32); coupling convs as VST_CONV_TF32X2 */
 
 int vst_revnet_create(const vst_revnet_config* cfg, vst_revnet** out);   /* RevResNet.__init__ :167-190 */
 void vst_revnet_destroy(vst_revnet* net);

@@ -20,7 +20,7 @@ with torch.no_grad():
     yr = O.revnet_inverse(sd, O.cwct_transfer(zr, zsr), **MODES[mode])
 e_ref = (xr_ref - x).abs()
 print("reference round trip: max %.3e mean %.3e" % (e_ref.max(), e_ref.mean()))
-for prec in ("fp32", "tf32", "tf32x2", "tf32x3"):
+for prec in ("fp32", "tf32", "tf32x2", "tf32x3", "f16x2"):
     net.precision = prec
     z = net(x.to(dev)); zs = net(s.to(dev))
     xr = net(z, forward=False)

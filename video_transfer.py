@@ -31,7 +31,7 @@ def build_parser():
     p.add_argument('--alpha_c', type=float, default=None)
     p.add_argument('--fps', type=int, default=10)
     p.add_argument('--auto_seg', action='store_true', default=False)
-    p.add_argument('--precision', type=str, default='tf32x2')
+    p.add_argument('--precision', type=str, default='f16x2')
     p.add_argument('--synthetic', type=str, default=None, help="HxWxF: F random frames, random-init weights")
     return p
 

@@ -62,7 +62,7 @@ class channel_reduction(nn.Module):
 
 class RevResNet(nn.Module):
     def __init__(self, nBlocks=[10, 10, 10], nStrides=[1, 2, 2], nChannels=[16, 64, 256], in_channel=3, mult=4,
-                 hidden_dim=16, sp_steps=2, kernel=3, precision="tf32x2"):
+                 hidden_dim=16, sp_steps=2, kernel=3, precision="f16x2"):
         super().__init__()
         if not nChannels:
             nChannels = [in_channel * 2, in_channel * 2 * 4, in_channel * 2 * 4 ** 2]

@@ -15,8 +15,8 @@ MAX_STAGES = 8
 MAX_LABELS = 256
 MAX_STYLES = 16
 
-CONV_FP32, CONV_TF32X3, CONV_TF32X2, CONV_TF32 = 0, 1, 2, 3
-PRECISIONS = {"fp32": CONV_FP32, "tf32x3": CONV_TF32X3, "tf32x2": CONV_TF32X2, "tf32": CONV_TF32}
+CONV_FP32, CONV_TF32X3, CONV_TF32X2, CONV_TF32, CONV_F16X2 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": CONV_FP32, "tf32x3": CONV_TF32X3, "tf32x2": CONV_TF32X2, "tf32": CONV_TF32, "f16x2": CONV_F16X2}
 
 
 class RevnetConfig(C.Structure):

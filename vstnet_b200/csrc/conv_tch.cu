@@ -1,0 +1,424 @@
+// conv_tch.cu — the kx-folded tcgen05 convolution of conv_tcx.cu with HALF-PRECISION SPLIT operands:
+//     x = hi + lo,  hi = fp16(x), lo = fp16(x - hi)   (22 significand bits, like the tf32 hi/lo split)
+//     w = fp16(w)                                     (11 significand bits, like tf32)
+//     D += hi * w ; D += lo * w                       (kind::f16 UMMA, fp32 accumulate in TMEM)
+// A kind::f16 UMMA consumes K = 16 channels for the same ~66-cycle operand-fetch-bound cost at which a
+// kind::tf32 UMMA consumes K = 8 (profiles/), and its operands are half as many bytes in shared memory
+// and in L2 (weights), so the tensor time and the weight traffic of these layers halve at equal accuracy.
+// Range: activations and weights of this network are O(1e-4 .. 1e2); fp16 subnormals (< 6e-5) lose
+// relative precision but stay within 3e-8 absolute, far below the fp32 noise of the outputs.
+//
+// Pipeline (per 16-channel chunk): TMA lands the raw fp32 P4 rows in a RAW ring; converter warps turn
+// them into the canonical K-major fp16 operand layout [k-half][row][pixel][8 halfs] (hi and lo) inside
+// an OPERAND ring slot, where a second TMA producer drops the chunk's fp16 weights; the UMMA issuer
+// consumes operand slots.  Two rings decouple the L2 latency (deep RAW ring) from operand storage.
+// Epilogue, tiling and the kx fold are those of conv_tcx.cu.
+#include <stdlib.h>
+#include "kernels.cuh"
+#include <cuda_fp16.h>
+#include "tc_ptx.cuh"
+
+namespace vst {
+
+template <int NC, int R, int TERMS>
+struct TchCfg {
+    static constexpr int NP = 3 * NC;               // UMMA N: (kx, cout)
+    static constexpr int TA = TERMS >= 2 ? 2 : 1;   // activation terms (hi [, lo])
+    static constexpr int TW = TERMS >= 3 ? 2 : 1;   // weight terms (hi [, lo])
+    static constexpr int PW = 128;                  // staged pixels per row = UMMA M
+    static constexpr int XS = 126;                  // outputs per tile row
+    static constexpr int ROWS = R + 2;
+    static constexpr int ROW_BYTES = PW * 16;       // one row of one 4-channel fp32 group == one row of one 8-channel fp16 k-half
+    static constexpr int RAW_BYTES = 4 * ROWS * ROW_BYTES;          // 16 channels fp32
+    static constexpr int A_TERM_BYTES = 2 * ROWS * ROW_BYTES;       // 16 channels fp16: [k-half][row][pixel][8 halfs]
+    static constexpr int A_BYTES = TA * A_TERM_BYTES;
+    static constexpr int B_TERM_BYTES = 3 * 2 * NP * 16;            // [ky][k-half][n'][8 halfs]
+    static constexpr int B_BYTES = TW * B_TERM_BYTES;
+    static constexpr int OP_BYTES = A_BYTES + B_BYTES;
+    static constexpr int ACC_COLS = R * NP;
+    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+    static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
+    static constexpr int EXCH_FLOATS = 2 * R * 4 * 2 * NC;          // [tile parity][row][warp quarter][side][cout]
+    static constexpr int AUX_BYTES = 2048 + EXCH_FLOATS * 4;        // barriers (1 KB) + bias (1 KB) + exchange
+    static constexpr int NO = 2;                                    // operand ring depth
+    static constexpr int NR_FIT = (226 * 1024 - AUX_BYTES - NO * OP_BYTES) / RAW_BYTES;
+    static constexpr int NR = NR_FIT > 4 ? 4 : NR_FIT;              // raw ring depth
+    static constexpr size_t SMEM = (size_t)NR * RAW_BYTES + (size_t)NO * OP_BYTES + AUX_BYTES + 128;
+    static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+    static_assert(NP % 16 == 0 && NP <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
+    static_assert(NR >= 2, "need at least a double-buffered raw ring");
+};
+
+// raw OIHW fp32 -> fp16 [cout tile][chunk16][term][ky][k-half (2)][n' = kx*NC + co][8 halfs]
+__global__ void pack_tch_weights_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Cin, int Cout, int NC,
+                                        int TW) {
+    const int NP = 3 * NC;
+    const size_t total = (size_t)(Cout / NC) * (Cin / 16) * TW * 3 * 2 * NP * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int e = (int)(r % 8); r /= 8;
+        const int n = (int)(r % NP); r /= NP;
+        const int kh = (int)(r % 2); r /= 2;
+        const int ky = (int)(r % 3); r /= 3;
+        const int term = (int)(r % TW); r /= TW;
+        const int chunk = (int)(r % (Cin / 16)); r /= (Cin / 16);
+        const int tile = (int)r;
+        const int kx = n / NC, co = tile * NC + (n - kx * NC), ci = chunk * 16 + kh * 8 + e;
+        const float v = w[((size_t)co * Cin + ci) * 9 + ky * 3 + kx];
+        const __half hi = __float2half_rn(v);
+        wp[i] = term == 0 ? hi : __float2half_rn(v - __half2float(hi));
+    }
+}
+
+int launch_pack_tch_weights(const float* w, float* wp, int Cin, int Cout, int NC, int terms, cudaStream_t st) {
+    const int TW = terms >= 3 ? 2 : 1;
+    const size_t total = (size_t)(Cout / NC) * (Cin / 16) * TW * 3 * 2 * (3 * NC) * 8;
+    pack_tch_weights_kernel<<<(int)std::min<size_t>((total + 255) / 256, 4096), 256, 0, st>>>(
+        w, reinterpret_cast<__half*>(wp), Cin, Cout, NC, TW);
+    return check_launch("pack_tch_weights");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), M=128, K=16
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+struct TchTiles {
+    int n_xt, n_yt, n_ct, n_tiles;
+    long long* trace;   // developer aid (VST_TC_TRACE): CTA 0 stamps clock64() per role event, 4096 slots per role
+};
+#define TCH_TRACE(role, idx) do { if (tl.trace && blockIdx.x == 0 && (idx) < 4096) tl.trace[(role) * 4096 + (idx)] = clock64(); } while (0)
+
+constexpr int TCH_THREADS = 480;   // 8 epilogue + 4 converter warps, activation producer, UMMA issuer, weight producer
+
+template <int NC, int R, int TERMS>
+__global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a, TchTiles tl) {
+    using Cfg = TchCfg<NC, R, TERMS>;
+    constexpr int NR = Cfg::NR, NO = Cfg::NO, PW = Cfg::PW, ROWS = Cfg::ROWS, NP = Cfg::NP, NACC = Cfg::NACC, XS = Cfg::XS;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* raw_base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t* op_base = raw_base + (size_t)NR * Cfg::RAW_BYTES;
+    uint64_t* bars = (uint64_t*)(op_base + (size_t)NO * Cfg::OP_BYTES);
+    uint64_t* raw_full = bars;                  // [NR]    activation producer arrive.expect_tx + TMA bytes
+    uint64_t* raw_empty = bars + 4;             // [NR]    128 converter threads
+    uint64_t* op_ready = bars + 8;              // [NO]    128 converter threads + weight producer arrive.expect_tx + TMA bytes
+    uint64_t* op_empty = bars + 12;             // [NO]    tcgen05.commit
+    uint64_t* acc_full = bars + 16;             // [NACC]  tcgen05.commit
+    uint64_t* acc_empty = bars + 18;            // [NACC]  256 epilogue threads
+    uint32_t* tmem_slot = (uint32_t*)(bars + 20);
+    float* bias_s = (float*)((uint8_t*)bars + 1024);
+    float* exch = bias_s + 256;                 // [2][R][4][2][NC]
+    for (int i = threadIdx.x; i < a.Cout && i < 256; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_chunks = a.Cin / 16;
+
+    if (tid == 0) {
+        for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
+        for (int s = 0; s < NO; ++s) { mbar_init(&op_ready[s], 129); mbar_init(&op_empty[s], 1); }
+        for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
+        fence_barrier_init();
+    }
+    if (warp == 13) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 12) {
+        // ================= activation producer (TMA): raw fp32 P4 rows of 16 channels -> RAW ring =================
+        if (lane == 0) {
+            const int Hp = a.Hin + 2, Wp = a.Win + 2;
+            const float4* in4 = reinterpret_cast<const float4*>(a.in);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
+                const int rest = t / tl.n_ct;
+                const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * R;
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    const int s = it % NR;
+                    mbar_wait(&raw_empty[s], ((it / NR) & 1) ^ 1);
+                    TCH_TRACE(0, it);
+                    uint8_t* A = raw_base + (size_t)s * Cfg::RAW_BYTES;
+                    mbar_arrive_expect_tx(&raw_full[s], Cfg::RAW_BYTES);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+#pragma unroll
+                        for (int row = 0; row < ROWS; ++row) {
+                            const int py = min(y0 + row, Hp - 1);     // padded row of image row y0-1+row
+                            // tile pixel p <-> padded column xs + p (image x = xs - 1 + p)
+                            bulk_g2s(A + (g * ROWS + row) * Cfg::ROW_BYTES,
+                                     in4 + ((size_t)(4 * c + g) * Hp + py) * Wp + xs, Cfg::ROW_BYTES, &raw_full[s]);
+                        }
+                }
+            }
+        }
+    } else if (warp == 14) {
+        // ================= weight producer (TMA): fp16 weights of the chunk -> operand slot =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
+                const int ct = t % tl.n_ct;
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)ct * n_chunks * Cfg::B_BYTES;
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    const int o = it % NO;
+                    mbar_wait(&op_empty[o], ((it / NO) & 1) ^ 1);
+                    uint8_t* B = op_base + (size_t)o * Cfg::OP_BYTES + Cfg::A_BYTES;
+                    mbar_arrive_expect_tx(&op_ready[o], Cfg::B_BYTES);
+                    bulk_g2s(B, wsrc + (size_t)c * Cfg::B_BYTES, Cfg::B_BYTES, &op_ready[o]);
+                }
+            }
+        }
+    } else if (warp == 13) {
+        // ================= UMMA issuer =================
+        if (lane == 0) {
+            // kind::f16: D = F32 (bit 4), A = B = F16 (format 0), N at bit 17, M at bit 24
+            constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t A_LBO = ROWS * Cfg::ROW_BYTES, B_LBO = NP * 16, SBO = 128;
+            uint32_t it = 0, tcount = 0;
+            for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
+                const uint32_t b = tcount % NACC;
+                mbar_wait(&acc_empty[b], ((tcount / NACC) & 1) ^ 1);
+                tc_fence_after();
+                TCH_TRACE(5, tcount);
+                const uint32_t acc = tmem_base + b * Cfg::ACC_COLS;
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    const int o = it % NO;
+                    mbar_wait(&op_ready[o], (it / NO) & 1);
+                    tc_fence_after();
+                    TCH_TRACE(3, it);
+                    const uint32_t Aaddr = smem_u32(op_base + (size_t)o * Cfg::OP_BYTES);
+                    const uint32_t Baddr = Aaddr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint64_t bh = make_desc(Baddr + ky * 2 * NP * 16, B_LBO, SBO);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const uint32_t aoff = (r + ky) * Cfg::ROW_BYTES;
+                            const uint32_t d = acc + r * NP;
+                            const uint32_t first = (c > 0 || ky > 0) ? 1u : 0u;
+                            umma_f16(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
+                            if (TERMS >= 2)
+                                umma_f16(d, make_desc(Aaddr + Cfg::A_TERM_BYTES + aoff, A_LBO, SBO), bh, IDESC, 1u);
+                            if (TERMS >= 3)
+                                umma_f16(d, make_desc(Aaddr + aoff, A_LBO, SBO),
+                                         make_desc(Baddr + Cfg::B_TERM_BYTES + ky * 2 * NP * 16, B_LBO, SBO), IDESC, 1u);
+                        }
+                    }
+                    umma_commit(&op_empty[o]);
+                    TCH_TRACE(4, it);
+                }
+                umma_commit(&acc_full[b]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 8 && warp < 12) {
+        // ================= converters: raw fp32 -> fp16 hi / lo in the K-major operand layout =================
+        // one item = 8 channels (two P4 groups) of one pixel: 32 bytes in, 16 (hi) + 16 (lo) bytes out
+        const int ctid = tid - 256;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
+            for (int c = 0; c < n_chunks; ++c, ++it) {
+                const int s = it % NR, o = it % NO;
+                mbar_wait(&raw_full[s], (it / NR) & 1);
+                mbar_wait(&op_empty[o], ((it / NO) & 1) ^ 1);          // the UMMAs that read this slot are done
+                if (ctid == 0) TCH_TRACE(1, it);
+                const float4* raw = reinterpret_cast<const float4*>(raw_base + (size_t)s * Cfg::RAW_BYTES);
+                uint4* hi = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES);
+                uint4* lo = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES + Cfg::A_TERM_BYTES);
+#pragma unroll 4
+                for (int i = ctid; i < 2 * ROWS * PW; i += 128) {
+                    const int kh = i / (ROWS * PW), rp = i - kh * (ROWS * PW);      // k-half, (row, pixel)
+                    const float4 u = raw[(2 * kh) * (ROWS * PW) + rp];
+                    const float4 v = raw[(2 * kh + 1) * (ROWS * PW) + rp];
+                    const float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+                    float h[8], l[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        h[e] = __half2float(__float2half_rn(x[e]));
+                        l[e] = x[e] - h[e];
+                    }
+                    hi[i] = make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
+                    if (Cfg::TA == 2)
+                        lo[i] = make_uint4(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]), pack_half2(l[6], l[7]));
+                }
+                fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core
+                mbar_arrive(&op_ready[o]);
+                mbar_arrive(&raw_empty[s]);
+                if (ctid == 0) TCH_TRACE(2, it);
+            }
+        }
+    } else if (warp < 8) {
+        // ================= epilogue: TMEM -> (lane-shifted sum over kx) -> ReLU -> P4 global =================
+        // lane l of warp (q, half) owns tile pixel m = 32q + l and the cout half `half`.
+        constexpr int HC = NC / 2;                         // couts per thread
+        constexpr int CH = HC >= 16 ? 16 : HC;             // couts per TMEM load
+        const int q = warp & 3, half = warp >> 2;
+        const int m = q * 32 + lane;
+        const float flo = (a.epi == EPI_RELU) ? 0.f : -INFINITY;
+        const int H = a.Hout, W = a.Wout, Wp = W + 2;
+        const size_t plane = p4_plane_px(H, W);
+        uint32_t tcount = 0;
+        for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
+            const int ct = t % tl.n_ct, rest = t / tl.n_ct;
+            const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * R;
+            const uint32_t b = tcount % NACC;
+            const int x = xs - 1 + m;
+            const bool xin = (m >= 1) && (m <= XS) && (x < W);
+            const int rows = min(R, H - y0);
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * Cfg::ACC_COLS + half * HC;
+            float* ex = exch + (size_t)(tcount & 1) * (R * 4 * 2 * NC);
+            mbar_wait(&acc_full[b], (tcount / NACC) & 1);
+            tc_fence_after();
+            if (tid == 0) TCH_TRACE(6, tcount);
+            // ---- phase 1: publish the partial sums a neighbouring warp needs (lane 31's kx=0, lane 0's kx=2)
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < HC; c0 += CH) {
+                    float v0[CH], v2[CH];
+                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0);
+                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
+                    if (lane == 31) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) ex[((r * 4 + q) * 2 + 0) * NC + half * HC + c0 + i] = v0[i];
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) ex[((r * 4 + q) * 2 + 1) * NC + half * HC + c0 + i] = v2[i];
+                    }
+                }
+            }
+            named_barrier(1, 256);
+            if (tid == 0) TCH_TRACE(7, 2 * tcount);
+            // ---- phase 2: out[m] = D[m-1][kx=0] + D[m][kx=1] + D[m+1][kx=2]
+            const bool lf = xin && (x == 1), rt = xin && (x == W - 2);
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) {
+                const int y = y0 + r;
+                const bool up = (y == 1), dn = (y == H - 2);
+#pragma unroll 1
+                for (int c0 = 0; c0 < HC; c0 += CH) {
+                    float v0[CH], v1[CH], v2[CH];
+                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0);
+                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 1 * NC + c0), v1);
+                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
+                    if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 0);
+                    const int cb = half * HC + c0;                  // first cout of this chunk (within the tile)
+                    const float* exl = ex + ((r * 4 + (q > 0 ? q - 1 : 0)) * 2 + 0) * NC + cb;   // left neighbour warp, lane 31
+                    const float* exr = ex + ((r * 4 + (q < 3 ? q + 1 : 3)) * 2 + 1) * NC + cb;   // right neighbour warp, lane 0
+                    // neighbour-warp values: warp-uniform addresses (broadcast loads), selected without branching
+                    float el[CH], er[CH];
+#pragma unroll
+                    for (int i = 0; i < CH; i += 4) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(exl + i);
+                        const float4 b4 = *reinterpret_cast<const float4*>(exr + i);
+                        el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
+                        er[i] = b4.x; er[i + 1] = b4.y; er[i + 2] = b4.z; er[i + 3] = b4.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const float ls = __shfl_up_sync(0xffffffffu, v0[i], 1);
+                        const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
+                        const float l = (lane == 0) ? el[i] : ls;
+                        const float rr = (lane == 31) ? er[i] : rs;
+                        v1[i] = (l + v1[i]) + rr;
+                    }
+                    if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 1);
+                    if (xin) {
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j) {
+                            const int g = (ct * NC + cb) / 4 + j;
+                            const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * g);
+                            float4 o;
+                            o.x = fmaxf(v1[4 * j] + bv.x, flo);
+                            o.y = fmaxf(v1[4 * j + 1] + bv.y, flo);
+                            o.z = fmaxf(v1[4 * j + 2] + bv.z, flo);
+                            o.w = fmaxf(v1[4 * j + 3] + bv.w, flo);
+                            float4* p = reinterpret_cast<float4*>(a.out) + (size_t)g * plane + (size_t)(y + 1) * Wp + (x + 1);
+                            *p = o;
+                            if (lf) p[-2] = o;                     // reflection border, inline and predicated
+                            if (rt) p[2] = o;
+                            if (up) {
+                                float4* qq = p - 2 * (size_t)Wp;
+                                *qq = o;
+                                if (lf) qq[-2] = o;
+                                if (rt) qq[2] = o;
+                            }
+                            if (dn) {
+                                float4* qq = p + 2 * (size_t)Wp;
+                                *qq = o;
+                                if (lf) qq[-2] = o;
+                                if (rt) qq[2] = o;
+                            }
+                        }
+                    }
+                    if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 2);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[b]);
+            if (tid == 0) TCH_TRACE(7, 2 * tcount + 1);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int NC, int R, int TERMS>
+static int launch_tch_cfg(const ConvArgs& a, cudaStream_t st) {
+    using Cfg = TchCfg<NC, R, TERMS>;
+    static bool attr_set = false;
+    auto kern = conv3x3_tch_kernel<NC, R, TERMS>;
+    if (!attr_set) {
+        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    TchTiles tl;
+    tl.n_xt = cdiv(a.Wout, Cfg::XS); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / NC;
+    tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;
+    tl.trace = tc_trace_buffer(a.Cin, a.Cout, st);
+    const int grid = std::min(tl.n_tiles, num_sms());
+    char cls[40];
+    snprintf(cls, sizeof(cls), "conv3x3_tch%d %d>%d", TERMS, a.Cin, a.Cout);
+    const double px = (double)a.Hout * a.Wout;
+    ProfScope prof(st, cls, 2.0 * 9 * a.Cin * a.Cout * px, 4.0 * ((double)a.Cin * a.Hin * a.Win + a.Cout * px));
+    kern<<<grid, TCH_THREADS, Cfg::SMEM, st>>>(a, tl);
+    return check_launch("conv3x3_tch");
+}
+
+bool tch_eligible(int Cin, int Cout, int stride) {
+    return stride == 1 && Cin % 16 == 0 && (Cout == 64 || Cout == 16);
+}
+
+// a.w must point at weights packed by launch_pack_tch_weights with NC = Cout and `terms`; epi is RELU or NONE
+int launch_conv3x3_tch(const ConvArgs& a, int terms, cudaStream_t st) {
+    VST_REQUIRE(tch_eligible(a.Cin, a.Cout, 1), "conv3x3_tch: shape %d>%d not eligible", a.Cin, a.Cout);
+    VST_REQUIRE(a.epi == EPI_RELU || a.epi == EPI_NONE, "conv3x3_tch has no coupling epilogue");
+    VST_REQUIRE(a.Hin == a.Hout && a.Win == a.Wout && a.Hin >= 2 && a.Win >= 2, "conv3x3_tch is stride 1, H,W >= 2");
+    if (a.Cout == 64) {
+        if (terms == 1) return launch_tch_cfg<64, 2, 1>(a, st);
+        if (terms == 2) return launch_tch_cfg<64, 2, 2>(a, st);
+        return launch_tch_cfg<64, 2, 3>(a, st);
+    }
+    if (terms == 1) return launch_tch_cfg<16, 4, 1>(a, st);
+    if (terms == 2) return launch_tch_cfg<16, 4, 2>(a, st);
+    return launch_tch_cfg<16, 4, 3>(a, st);
+}
+
+}  // namespace vst

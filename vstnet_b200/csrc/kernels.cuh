@@ -142,6 +142,11 @@ bool tcx_eligible(int Cin, int Cout, int stride);
 int launch_pack_tcx_weights(const float* w, float* wp, int Cin, int Cout, int NC, int terms, cudaStream_t st);
 int launch_conv3x3_tcx(const ConvArgs& a, int terms, cudaStream_t st);
 
+// the same with half-precision split operands (kind::f16, K = 16 per UMMA), conv_tch.cu
+bool tch_eligible(int Cin, int Cout, int stride);
+int launch_pack_tch_weights(const float* w, float* wp, int Cin, int Cout, int NC, int terms, cudaStream_t st);
+int launch_conv3x3_tch(const ConvArgs& a, int terms, cudaStream_t st);
+
 // layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
 int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st);   // NCHW -> P4
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st);           // P4 -> NCHW

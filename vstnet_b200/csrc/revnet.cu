@@ -19,6 +19,7 @@ struct ConvDesc {
     size_t pk_w, pk_b;    // float offsets into the packed buffer
     bool tc;              // eligible for the tcgen05 implicit-GEMM kernel
     bool tcx;             // ... in its kx-folded form (no coupling operand: conv1 / conv2 of a block)
+    bool tch;             // ... kx-folded with fp16 split operands (precision f16x2)
     size_t pk_tc;         // float offset of the tensor-core weight pack (sized for hi+lo terms)
 };
 struct BlockDesc {
@@ -58,6 +59,7 @@ static void add_block(vst_revnet* n, std::vector<BlockDesc>& dst, int channel, i
         c.pk_b = n->packed_floats; n->packed_floats += (size_t)c.CoutPad;
         c.tc = tc_eligible(c.Cin, c.Cout, c.stride);
         c.tcx = k < 2 && tcx_eligible(c.Cin, c.Cout, c.stride);
+        c.tch = k < 2 && tch_eligible(c.Cin, c.Cout, c.stride);
         c.pk_tc = n->packed_floats;
         if (c.tc) n->packed_floats += tc_packed_floats(c.Cin, c.Cout, tc_tile_n(c.Cout), 3);
     }
@@ -118,13 +120,18 @@ static ConvArgs conv_args(const ConvDesc& c, const float* packed, const float* i
 }
 
 static int tc_terms(int precision) {
-    return precision == VST_CONV_TF32 ? 1 : precision == VST_CONV_TF32X2 ? 2 : precision == VST_CONV_TF32X3 ? 3 : 0;
+    return precision == VST_CONV_TF32 ? 1 : (precision == VST_CONV_TF32X2 || precision == VST_CONV_F16X2) ? 2
+           : precision == VST_CONV_TF32X3 ? 3 : 0;
 }
 
 static int run_conv(const vst_revnet* n, const ConvDesc& c, const float* packed, const float* in, int Hin, int Win,
                     float* out, const float* res, int epi, cudaStream_t st) {
     ConvArgs a = conv_args(c, packed, in, Hin, Win, out, res, epi);
     const int terms = tc_terms(n->precision);
+    if (n->precision == VST_CONV_F16X2 && c.tch && (epi == EPI_RELU || epi == EPI_NONE)) {
+        a.w = packed + c.pk_tc;
+        return launch_conv3x3_tch(a, terms, st);
+    }
     if (terms > 0 && c.tcx && (epi == EPI_RELU || epi == EPI_NONE)) {
         a.w = packed + c.pk_tc;
         return launch_conv3x3_tcx(a, terms, st);
@@ -268,7 +275,7 @@ extern "C" void vst_revnet_destroy(vst_revnet* net) { delete net; }
 
 extern "C" int vst_revnet_set_precision(vst_revnet* net, int mode) {
     VST_REQUIRE(net, "null net");
-    VST_REQUIRE(mode >= VST_CONV_FP32 && mode <= VST_CONV_TF32, "unknown precision mode %d", mode);
+    VST_REQUIRE(mode >= VST_CONV_FP32 && mode <= VST_CONV_F16X2, "unknown precision mode %d", mode);
     net->precision = mode;
     return 0;
 }
@@ -289,7 +296,11 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
                                              c.CoutPad, (cudaStream_t)stream))
                     return 1;
                 const int terms = tc_terms(net->precision);
-                if (terms > 0 && c.tcx) {
+                if (net->precision == VST_CONV_F16X2 && c.tch) {
+                    if (launch_pack_tch_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, c.Cout, terms,
+                                                (cudaStream_t)stream))
+                        return 1;
+                } else if (terms > 0 && c.tcx) {
                     if (launch_pack_tcx_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, c.Cout, terms,
                                                 (cudaStream_t)stream))
                         return 1;
