@@ -27,6 +27,7 @@
 //     warps 8-11 converters, warp 12 TMA producer, warp 13 UMMA issuer + TMEM owner.
 #include <stdlib.h>
 #include "kernels.cuh"
+#include <cuda_fp16.h>
 #include "tc_ptx.cuh"
 
 namespace vst {
@@ -34,8 +35,9 @@ namespace vst {
 // ------------------------------------------------------------------------------------------
 // configuration
 // ------------------------------------------------------------------------------------------
-template <int N, int R, int TERMS>
+template <int N, int R, int TERMS, bool HALF = false>
 struct TcCfg {
+    static constexpr int KCH = HALF ? 16 : 8;       // input channels per pipeline stage (one UMMA K)
     static constexpr int TA = TERMS >= 2 ? 2 : 1;   // activation terms staged (hi [, lo])
     static constexpr int TW = TERMS >= 3 ? 2 : 1;   // weight terms staged (hi [, lo])
     static constexpr int PW = 130;                  // staged pixels per halo row (128 + 2)
@@ -101,9 +103,22 @@ struct TcTiles {
 
 constexpr int TC_THREADS = 512;   // 4 warpgroups: 2 x epilogue, converters, {operand producer, UMMA issuer, 2 idle}
 
-template <int N, int R, int TERMS>
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), M=128, K=16
+__device__ __forceinline__ void umma_f16_tc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// HALF = true: the input is an H8 split-half tensor (kernels.cuh): hi and lo rows arrive by TMA already in
+// the K-major fp16 operand layout, there is no converter stage, and the UMMAs are kind::f16 with K = 16.
+template <int N, int R, int TERMS, bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, TcTiles tl) {
-    using Cfg = TcCfg<N, R, TERMS>;
+    using Cfg = TcCfg<N, R, TERMS, HALF>;
     constexpr int NS = Cfg::NS, PW = Cfg::PW, ROWS = Cfg::ROWS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* stage_base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
     for (int i = threadIdx.x; i < a.Cout && i < 256; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_chunks = a.Cin / 8;
+    const int n_chunks = a.Cin / Cfg::KCH;
     const bool hot = a.epi <= EPI_SUB;                       // branch-free epilogue; squeeze modes use the generic one
     const bool coupled = a.epi == EPI_ADD || a.epi == EPI_SUB;
 
@@ -152,22 +167,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                     mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
                     TC_TRACE(0, it);
                     uint8_t* A = stage_base + (size_t)s * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&loaded[s], Cfg::A_TERM_BYTES + Cfg::B_BYTES);
+                    constexpr int NT = HALF ? Cfg::TA : 1;            // tensors to fetch: raw fp32 | hi, lo
+                    mbar_arrive_expect_tx(&loaded[s], NT * Cfg::A_TERM_BYTES + Cfg::B_BYTES);
 #pragma unroll
-                    for (int g = 0; g < 2; ++g)
+                    for (int term = 0; term < NT; ++term) {
+                        // H8: the lo planes follow the Cin/8 hi planes; both are addressed like P4 groups
+                        const float4* src = in4 + (size_t)term * (a.Cin / 8) * Hp * Wp;
 #pragma unroll
-                        for (int row = 0; row < ROWS; ++row) {
-                            const int py = min(y0 + row, Hp - 1);     // padded row of image row y0-1+row
-                            bulk_g2s(A + (g * ROWS + row) * Cfg::ROW_BYTES,
-                                     in4 + ((size_t)(2 * c + g) * Hp + py) * Wp + x0, Cfg::ROW_BYTES, &loaded[s]);
-                        }
+                        for (int g = 0; g < 2; ++g)
+#pragma unroll
+                            for (int row = 0; row < ROWS; ++row) {
+                                const int py = min(y0 + row, Hp - 1);     // padded row of image row y0-1+row
+                                bulk_g2s(A + term * Cfg::A_TERM_BYTES + (g * ROWS + row) * Cfg::ROW_BYTES,
+                                         src + ((size_t)(2 * c + g) * Hp + py) * Wp + x0, Cfg::ROW_BYTES, &loaded[s]);
+                            }
+                    }
                     bulk_g2s(A + Cfg::A_BYTES, wsrc + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &loaded[s]);
                 }
             }
         } else if (warp == 13 && lane == 0) {
             // ================= UMMA issuer =================
-            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            // instruction descriptor: D = F32 (bit 4); A, B = TF32 (format 2) | F16 (format 0); N at bit 17, M at bit 24
+            constexpr uint32_t IDESC = (1u << 4) | (HALF ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t A_LBO = ROWS * Cfg::ROW_BYTES, B_LBO = N * 16, SBO = 128;
+            uint64_t* const opbar = HALF ? loaded : ready;      // no converter stage for pre-split operands
             uint32_t it = 0, tcount = 0;
             for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
                 const uint32_t b = tcount & 1;
@@ -177,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                 const uint32_t acc = tmem_base + b * Cfg::ACC_COLS;
                 for (int c = 0; c < n_chunks; ++c, ++it) {
                     const int s = it % NS;
-                    mbar_wait(&ready[s], (it / NS) & 1);
+                    mbar_wait(&opbar[s], (it / NS) & 1);
                     tc_fence_after();
                     TC_TRACE(3, it);
                     const uint32_t Aaddr = smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
@@ -191,12 +214,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                             const uint32_t aoff = ((r + ky) * PW + kx) * 16;
                             const uint32_t d = acc + r * N;
                             const uint32_t first = (c > 0 || tap > 0) ? 1u : 0u;
-                            umma_tf32(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
-                            if (TERMS >= 2)
-                                umma_tf32(d, make_desc(Aaddr + Cfg::A_TERM_BYTES + aoff, A_LBO, SBO), bh, IDESC, 1u);
-                            if (TERMS >= 3)
-                                umma_tf32(d, make_desc(Aaddr + aoff, A_LBO, SBO),
-                                          make_desc(Baddr + Cfg::B_TERM_BYTES + tap * 2 * N * 16, B_LBO, SBO), IDESC, 1u);
+                            if (HALF) {
+                                umma_f16_tc(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
+                                if (TERMS >= 2)
+                                    umma_f16_tc(d, make_desc(Aaddr + Cfg::A_TERM_BYTES + aoff, A_LBO, SBO), bh, IDESC, 1u);
+                            } else {
+                                umma_tf32(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
+                                if (TERMS >= 2)
+                                    umma_tf32(d, make_desc(Aaddr + Cfg::A_TERM_BYTES + aoff, A_LBO, SBO), bh, IDESC, 1u);
+                                if (TERMS >= 3)
+                                    umma_tf32(d, make_desc(Aaddr + aoff, A_LBO, SBO),
+                                              make_desc(Baddr + Cfg::B_TERM_BYTES + tap * 2 * N * 16, B_LBO, SBO), IDESC, 1u);
+                            }
                         }
                     }
                     umma_commit(&empty[s]);      // smem stage reusable once these UMMAs have read it
@@ -211,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         const int ctid = tid - 256;
         uint32_t it = 0;
-        for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; !HALF && t < tl.n_tiles; t += gridDim.x) {
             for (int c = 0; c < n_chunks; ++c, ++it) {
                 const int s = it % NS;
                 mbar_wait(&loaded[s], (it / NS) & 1);
@@ -244,6 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
         const int q = warp & 3, half = warp >> 2;
         const float sgn = (a.epi == EPI_SUB) ? -1.f : 1.f;
         const float flo = (a.epi == EPI_RELU) ? 0.f : -INFINITY;
+        constexpr float unscale = HALF ? 1.0f / VST_HALF_SCALE : 1.0f;    // H8 operands carry VST_HALF_SCALE * x
         const int H = a.Hout, W = a.Wout, Wp = W + 2;
         const size_t plane = p4_plane_px(H, W);
         uint32_t tcount = 0;
@@ -285,10 +315,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                                     const int j = c0 / 4 + jj;
                                     const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * (g0 + j));
                                     float4 o = res[r][j];
-                                    o.x += fmaxf((v[4 * jj] + bv.x) * sgn, flo);
-                                    o.y += fmaxf((v[4 * jj + 1] + bv.y) * sgn, flo);
-                                    o.z += fmaxf((v[4 * jj + 2] + bv.z) * sgn, flo);
-                                    o.w += fmaxf((v[4 * jj + 3] + bv.w) * sgn, flo);
+                                    o.x += fmaxf((v[4 * jj] * unscale + bv.x) * sgn, flo);
+                                    o.y += fmaxf((v[4 * jj + 1] * unscale + bv.y) * sgn, flo);
+                                    o.z += fmaxf((v[4 * jj + 2] * unscale + bv.z) * sgn, flo);
+                                    o.w += fmaxf((v[4 * jj + 3] * unscale + bv.w) * sgn, flo);
                                     float4* p = outp + (size_t)j * plane + (size_t)r * Wp;
                                     *p = o;
                                     if (lf) p[-2] = o;                 // reflection border, inline and predicated
@@ -327,8 +357,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                             for (int jj = 0; jj < CH / 4; ++jj) {
                                 const int g = g0 + c0 / 4 + jj;
                                 const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * g);
-                                conv_epilogue(a, g, y, x, make_float4(v[4 * jj] + bv.x, v[4 * jj + 1] + bv.y,
-                                                                      v[4 * jj + 2] + bv.z, v[4 * jj + 3] + bv.w));
+                                conv_epilogue(a, g, y, x, make_float4(v[4 * jj] * unscale + bv.x, v[4 * jj + 1] * unscale + bv.y,
+                                                                      v[4 * jj + 2] * unscale + bv.z, v[4 * jj + 3] * unscale + bv.w));
                             }
                         }
                     }
@@ -365,11 +395,11 @@ long long* tc_trace_buffer(int Cin, int Cout, cudaStream_t st) {
     return buf;
 }
 
-template <int N, int R, int TERMS>
+template <int N, int R, int TERMS, bool HALF = false>
 static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
-    using Cfg = TcCfg<N, R, TERMS>;
+    using Cfg = TcCfg<N, R, TERMS, HALF>;
     static bool attr_set = false;
-    auto kern = conv3x3_tc_kernel<N, R, TERMS>;
+    auto kern = conv3x3_tc_kernel<N, R, TERMS, HALF>;
     if (!attr_set) {
         VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
@@ -380,7 +410,7 @@ static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
     tl.trace = (a.epi <= EPI_SUB) ? tc_trace_buffer(a.Cin, a.Cout, st) : nullptr;
     const int grid = std::min(tl.n_tiles, num_sms());
     char cls[40];
-    snprintf(cls, sizeof(cls), "conv3x3_tc%d %d>%d", TERMS, a.Cin, a.Cout);
+    snprintf(cls, sizeof(cls), HALF ? "conv3x3_tcH%d %d>%d" : "conv3x3_tc%d %d>%d", TERMS, a.Cin, a.Cout);
     const double px = (double)a.Hout * a.Wout;
     const bool coupled = a.epi >= EPI_ADD;
     ProfScope prof(st, cls, 2.0 * 9 * a.Cin * a.Cout * px,
@@ -425,6 +455,41 @@ int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st) {
     if (terms == 1) return launch_tc_cfg<16, 4, 1>(a, st);
     if (terms == 2) return launch_tc_cfg<16, 4, 2>(a, st);
     return launch_tc_cfg<16, 4, 3>(a, st);
+}
+
+bool tc_half_eligible(int Cin, int Cout, int stride) { return tc_eligible(Cin, Cout, stride) && Cin % 16 == 0; }
+
+// raw OIHW fp32 -> fp16 [cout tile][chunk16][tap][k-half (2)][n][8 halfs]   (one weight term: w = fp16(w))
+__global__ void pack_tc_half_weights_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Cin, int Cout, int N) {
+    const size_t total = (size_t)(Cout / N) * (Cin / 16) * 9 * 2 * N * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int e = (int)(r % 8); r /= 8;
+        const int n = (int)(r % N); r /= N;
+        const int kh = (int)(r % 2); r /= 2;
+        const int tap = (int)(r % 9); r /= 9;
+        const int chunk = (int)(r % (Cin / 16)); r /= (Cin / 16);
+        const int tile = (int)r;
+        const int co = tile * N + n, ci = chunk * 16 + kh * 8 + e;
+        wp[i] = __float2half_rn(w[((size_t)co * Cin + ci) * 9 + tap]);
+    }
+}
+
+int launch_pack_tc_half_weights(const float* w, float* wp, int Cin, int Cout, int N, cudaStream_t st) {
+    const size_t total = (size_t)(Cout / N) * (Cin / 16) * 9 * 2 * N * 8;
+    pack_tc_half_weights_kernel<<<(int)std::min<size_t>((total + 255) / 256, 4096), 256, 0, st>>>(
+        w, reinterpret_cast<__half*>(wp), Cin, Cout, N);
+    return check_launch("pack_tc_half_weights");
+}
+
+// a.in is an H8 split-half tensor; a.w packed by launch_pack_tc_half_weights with N = tc_tile_n(Cout)
+int launch_conv3x3_tc_half(const ConvArgs& a, cudaStream_t st) {
+    VST_REQUIRE(tc_half_eligible(a.Cin, a.Cout, 1), "conv3x3_tc_half: shape %d>%d not eligible", a.Cin, a.Cout);
+    VST_REQUIRE(a.Hin == a.Hout && a.Win == a.Wout && a.Hin >= 2 && a.Win >= 2, "conv3x3_tc_half is stride 1, H,W >= 2");
+    const int N = tc_tile_n(a.Cout);
+    if (N == 128) return launch_tc_cfg<128, 2, 2, true>(a, st);
+    if (N == 64) return launch_tc_cfg<64, 4, 2, true>(a, st);
+    return launch_tc_cfg<16, 4, 2, true>(a, st);
 }
 
 }  // namespace vst

@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                     const int kh = i / (ROWS * PW), rp = i - kh * (ROWS * PW);      // k-half, (row, pixel)
                     const float4 u = raw[(2 * kh) * (ROWS * PW) + rp];
                     const float4 v = raw[(2 * kh + 1) * (ROWS * PW) + rp];
-                    const float x[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+                    const float x[8] = {u.x * VST_HALF_SCALE, u.y * VST_HALF_SCALE, u.z * VST_HALF_SCALE, u.w * VST_HALF_SCALE,
+                                        v.x * VST_HALF_SCALE, v.y * VST_HALF_SCALE, v.z * VST_HALF_SCALE, v.w * VST_HALF_SCALE};
                     float h[8], l[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
@@ -332,10 +333,51 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                         const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
                         const float l = (lane == 0) ? el[i] : ls;
                         const float rr = (lane == 31) ? er[i] : rs;
-                        v1[i] = (l + v1[i]) + rr;
+                        v1[i] = ((l + v1[i]) + rr) * (1.0f / VST_HALF_SCALE);
                     }
                     if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 1);
-                    if (xin) {
+                    if (xin && a.out_split) {
+                        // H8 split-half output (feeds a kind::f16 conv): 8 channels = one 16-byte unit of hi and of lo
+#pragma unroll
+                        for (int j = 0; j < CH / 8; ++j) {
+                            const int g8 = (ct * NC + cb) / 8 + j;
+                            float o[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                o[e] = fmaxf(v1[8 * j + e] + bias_s[ct * NC + cb + 8 * j + e], flo) * VST_HALF_SCALE;
+                            uint32_t hw[4], lw[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __half2 hh = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+                                const float2 hf = __half22float2(hh);
+                                hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                                lw[e] = pack_half2(o[2 * e] - hf.x, o[2 * e + 1] - hf.y);
+                            }
+                            const uint4 hv = make_uint4(hw[0], hw[1], hw[2], hw[3]), lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            const size_t lo_off = (size_t)(a.Cout / 8) * plane;          // lo planes follow the hi planes
+                            uint4* p = reinterpret_cast<uint4*>(a.out) + (size_t)g8 * plane + (size_t)(y + 1) * Wp + (x + 1);
+#pragma unroll
+                            for (int part = 0; part < 2; ++part) {
+                                uint4* pp = p + (part ? lo_off : 0);
+                                const uint4 val = part ? lv : hv;
+                                *pp = val;
+                                if (lf) pp[-2] = val;
+                                if (rt) pp[2] = val;
+                                if (up) {
+                                    uint4* qq = pp - 2 * (size_t)Wp;
+                                    *qq = val;
+                                    if (lf) qq[-2] = val;
+                                    if (rt) qq[2] = val;
+                                }
+                                if (dn) {
+                                    uint4* qq = pp + 2 * (size_t)Wp;
+                                    *qq = val;
+                                    if (lf) qq[-2] = val;
+                                    if (rt) qq[2] = val;
+                                }
+                            }
+                        }
+                    } else if (xin) {
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) {
                             const int g = (ct * NC + cb) / 4 + j;

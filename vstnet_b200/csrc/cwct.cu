@@ -52,7 +52,11 @@ __global__ void pivot_kernel(const float* __restrict__ feat, long long n, float*
 }
 
 // ---- C <= 32: every warp owns a private 32x32 Gram in registers (lane: 4 rows x 8 cols) and
-// streams its own contiguous pixel range through a private smem sub-tile.
+// streams its own contiguous pixel range through a private smem sub-tile.  fp32 products are summed
+// in fp32 over runs of at most 256 pixels and folded into fp64; the unmasked kernel keeps the fp64
+// partials in registers, reduces the 8 warps of the CTA through shared memory and issues ONE set of
+// global fp64 atomics per CTA (the per-warp flushes of an earlier version serialised on ~1000 hot
+// addresses and cost 4x the HBM time of the pass).
 template <bool MASKED>
 __global__ void __launch_bounds__(256) gram32_kernel(const float* __restrict__ feat, int C, long long n,
                                                      const uint8_t* __restrict__ labels, int L, StatsView sv,
@@ -68,24 +72,38 @@ __global__ void __launch_bounds__(256) gram32_kernel(const float* __restrict__ f
 
     float acc[4][8];
     float sacc = 0.f;
+    double dacc[MASKED ? 1 : 4][MASKED ? 1 : 8];     // unmasked: fp64 partial Gram of this warp
+    double dsum = 0.0, dcnt = 0.0;
     int cnt = 0, cur = MASKED ? -1 : 0, since = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+        for (int b = 0; b < 8; ++b) {
+            acc[a][b] = 0.f;
+            if (!MASKED) dacc[a][b] = 0.0;
+        }
 
     auto flush = [&](int l) {
-        if (l >= 0 && l < L && cnt > 0) {
-            double* g = sv.gram + (size_t)l * C * C;
+        if (MASKED) {
+            if (l >= 0 && l < L && cnt > 0) {
+                double* g = sv.gram + (size_t)l * C * C;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        int i = gi * 4 + a, j = gj * 4 + b;
+                        if (i < C && j < C) atomicAdd(g + (size_t)i * C + j, (double)acc[a][b]);
+                    }
+                if (lane < C) atomicAdd(sv.sum + (size_t)l * C + lane, (double)sacc);
+                if (lane == 0) atomicAdd(sv.count + l, (double)cnt);
+            }
+        } else {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    int i = gi * 4 + a, j = gj * 4 + b;
-                    if (i < C && j < C) atomicAdd(g + (size_t)i * C + j, (double)acc[a][b]);
-                }
-            if (lane < C) atomicAdd(sv.sum + (size_t)l * C + lane, (double)sacc);
-            if (lane == 0) atomicAdd(sv.count + l, (double)cnt);
+                for (int b = 0; b < 8; ++b) dacc[a][b] += (double)acc[a][b];
+            dsum += (double)sacc;
+            dcnt += (double)cnt;
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -129,9 +147,35 @@ __global__ void __launch_bounds__(256) gram32_kernel(const float* __restrict__ f
         }
         __syncwarp();
         since += 32;
-        if (since >= 1024) flush(cur);   // bound the fp32 run length; the cross-run sum is fp64
+        if (since >= (MASKED ? 1024 : 256)) flush(cur);   // bound the fp32 run length; the cross-run sum is fp64
     }
     flush(cur);
+
+    if (!MASKED) {
+        // CTA-level fp64 reduction through the (now idle) tile storage, then one set of global atomics
+        __syncthreads();
+        double* red = reinterpret_cast<double*>(&tile[0][0][0][0]);          // 8*8*33*4 floats = 33 KB >= (1024 + 33) doubles
+        for (int w = 0; w < 8; ++w) {
+            if (warp == w) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const int idx = (gi * 4 + a) * 32 + gj * 4 + b;
+                        red[idx] = (w == 0 ? 0.0 : red[idx]) + dacc[a][b];
+                    }
+                red[1024 + lane] = (w == 0 ? 0.0 : red[1024 + lane]) + dsum;
+                if (lane == 0) red[1056] = (w == 0 ? 0.0 : red[1056]) + dcnt;
+            }
+            __syncthreads();
+        }
+        for (int e = threadIdx.x; e < 1024; e += 256) {
+            const int i = e >> 5, j = e & 31;
+            if (i < C && j < C) atomicAdd(sv.gram + (size_t)i * C + j, red[e]);
+        }
+        if (threadIdx.x < C) atomicAdd(sv.sum + threadIdx.x, red[1024 + threadIdx.x]);
+        if (threadIdx.x == 0) atomicAdd(sv.count, red[1056]);
+    }
 }
 
 // ---- 32 < C <= 128: the CTA owns one 128x128 Gram (thread: 8 rows x 8 cols) and streams a
@@ -446,10 +490,20 @@ __global__ void __launch_bounds__(256) apply_kernel(const float* __restrict__ fe
             }
             uni = __syncthreads_and(mine_ok) ? l0 : -1;
         }
-        // ---- stage x (raw)
-        for (int i = tid; i < CP * PX; i += 256) {
-            int k = i / PX, px = i - k * PX;
-            xs[i] = (k < C && px < npx) ? __ldg(feat + (size_t)k * n + p0 + px) : 0.f;
+        // ---- stage x (raw); 16-byte loads when the rows are 16-byte aligned and the tile is full
+        const bool vec = ((n & 3) == 0) && npx == PX && ((((uintptr_t)feat | (uintptr_t)out) & 15) == 0);
+        if (vec) {
+            for (int i = tid; i < CP * (PX / 4); i += 256) {
+                int k = i / (PX / 4), p4 = i - k * (PX / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < C) v = __ldg(reinterpret_cast<const float4*>(feat + (size_t)k * n + p0) + p4);
+                reinterpret_cast<float4*>(xs + k * PX)[p4] = v;
+            }
+        } else {
+            for (int i = tid; i < CP * PX; i += 256) {
+                int k = i / PX, px = i - k * PX;
+                xs[i] = (k < C && px < npx) ? __ldg(feat + (size_t)k * n + p0 + px) : 0.f;
+            }
         }
         if (uni >= 0 && uni != cached) {
             const int l = uni < L ? uni : 0;
@@ -502,10 +556,15 @@ __global__ void __launch_bounds__(256) apply_kernel(const float* __restrict__ fe
                 const int c = cg * 8 + a;
                 if (c >= C) continue;
                 const float bt = be_s[c];
+                if (vec) {
+                    *reinterpret_cast<float4*>(out + (size_t)c * n + p0 + pg * 4) =
+                        make_float4(acc[a][0] + bt, acc[a][1] + bt, acc[a][2] + bt, acc[a][3] + bt);
+                } else {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int px = pg * 4 + b;
-                    if (px < npx) out[(size_t)c * n + p0 + px] = acc[a][b] + bt;
+                    for (int b = 0; b < 4; ++b) {
+                        const int px = pg * 4 + b;
+                        if (px < npx) out[(size_t)c * n + p0 + px] = acc[a][b] + bt;
+                    }
                 }
             }
         } else {
@@ -581,7 +640,7 @@ extern "C" int vst_cwct_stats(const float* feat, int C, long long n, const uint8
     ProfScope prof(st, C <= 32 ? "cwct_gram c32" : "cwct_gram c128", 2.0 * C * C * (double)n,
                    4.0 * C * (double)n + (labels ? (double)n : 0.0));
     if (C <= 32) {
-        int grid = sms * 3;
+        int grid = labels ? sms * 3 : sms * 2;
         long long warps = (long long)grid * 8;
         long long chunk = ((n + warps - 1) / warps + 31) / 32 * 32;
         grid = (int)((n + chunk * 8 - 1) / (chunk * 8));

@@ -48,6 +48,8 @@ __device__ __forceinline__ void p4_store(float4* plane, int H, int W, int y, int
 }
 #endif
 
+#define VST_HALF_SCALE 64.0f
+
 enum ConvEpi {
     EPI_RELU = 0,       // out = relu(conv + bias)
     EPI_NONE = 1,       // out = conv + bias
@@ -65,7 +67,18 @@ struct ConvArgs {
     float* out;         // P4
     int Cin, Cout, CoutPad, Hin, Win, Hout, Wout;
     int epi;
+    int out_split;      // conv_tch only: write the result as split fp16 (hi planes, then lo planes; see below)
 };
+
+// "H8" split-half layout of a bottleneck tensor that only feeds a tensor-core conv (precision f16x2):
+//     hi [C/8][H+2][W+2][8 halfs]  followed by  lo [C/8][H+2][W+2][8 halfs],   x = hi + lo
+// fp16 has only 5 exponent bits: for |x| < 0.1 the remainder x - hi (~ x * 2^-12) would fall into the fp16
+// subnormals and lose its low bits.  The split therefore works on VST_HALF_SCALE * x (a power of two:
+// exact), which keeps lo normal down to |x| ~ 4e-3 and still leaves |x| < 1000 representable; the
+// consuming kernel multiplies its fp32 accumulators by 1 / VST_HALF_SCALE (exact) in the epilogue.
+// One pixel of one 8-channel group is again a 16-byte unit, so a tensor in this layout is addressed
+// exactly like a P4 tensor with C/8 "groups" (border included) and occupies the same number of bytes as
+// the fp32 P4 tensor it replaces.
 
 #ifdef __CUDACC__
 // Fused epilogue shared by the FFMA and tcgen05 kernels, in two halves so that callers can issue
@@ -135,6 +148,10 @@ int tc_tile_n(int Cout);
 size_t tc_packed_floats(int Cin, int Cout, int N, int terms);
 int launch_pack_tc_weights(const float* w, float* wp, int Cin, int Cout, int N, int terms, cudaStream_t st);
 int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st);
+// ... with fp16 split operands: a.in is an H8 tensor, weights packed by launch_pack_tch3_weights (2 terms)
+bool tc_half_eligible(int Cin, int Cout, int stride);
+int launch_pack_tc_half_weights(const float* w, float* wp, int Cin, int Cout, int N, cudaStream_t st);
+int launch_conv3x3_tc_half(const ConvArgs& a, cudaStream_t st);
 long long* tc_trace_buffer(int Cin, int Cout, cudaStream_t st);   // developer aid, conv_tc.cu
 
 // kx-folded tensor-core path for the convs without a coupling operand (ReLU / plain epilogue), conv_tcx.cu

@@ -116,7 +116,14 @@ static ConvArgs conv_args(const ConvDesc& c, const float* packed, const float* i
     a.Cin = c.Cin; a.Cout = c.Cout; a.CoutPad = c.CoutPad;
     a.Hin = Hin; a.Win = Win; a.Hout = Hin / c.stride; a.Wout = Win / c.stride;
     a.epi = epi;
+    a.out_split = 0;
     return a;
+}
+
+// precision f16x2: conv2 (kx-folded fp16 kernel) hands its result to conv3 as an H8 split-half tensor, and
+// conv3 runs its kind::f16 variant on it (no converter stage, half the weight bytes)
+static bool block_split_t2(const vst_revnet* n, const BlockDesc& b) {
+    return n->precision == VST_CONV_F16X2 && b.conv[1].tch && b.conv[2].tc && tc_half_eligible(b.conv[2].Cin, b.conv[2].Cout, 1);
 }
 
 static int tc_terms(int precision) {
@@ -125,9 +132,14 @@ static int tc_terms(int precision) {
 }
 
 static int run_conv(const vst_revnet* n, const ConvDesc& c, const float* packed, const float* in, int Hin, int Win,
-                    float* out, const float* res, int epi, cudaStream_t st) {
+                    float* out, const float* res, int epi, cudaStream_t st, bool out_split = false, bool in_split = false) {
     ConvArgs a = conv_args(c, packed, in, Hin, Win, out, res, epi);
     const int terms = tc_terms(n->precision);
+    a.out_split = out_split ? 1 : 0;
+    if (in_split) {
+        a.w = packed + c.pk_tc;
+        return launch_conv3x3_tc_half(a, st);
+    }
     if (n->precision == VST_CONV_F16X2 && c.tch && (epi == EPI_RELU || epi == EPI_NONE)) {
         a.w = packed + c.pk_tc;
         return launch_conv3x3_tch(a, terms, st);
@@ -159,8 +171,9 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
         return launch_rev_block16(a, st);
     }
     if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, st)) return 1;
-    if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, st)) return 1;
-    if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, st)) return 1;
+    const bool split = block_split_t2(n, b);
+    if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, st, split, false)) return 1;
+    if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, st, false, split)) return 1;
     return 0;
 }
 
@@ -296,7 +309,11 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
                                              c.CoutPad, (cudaStream_t)stream))
                     return 1;
                 const int terms = tc_terms(net->precision);
-                if (net->precision == VST_CONV_F16X2 && c.tch) {
+                if (k == 2 && block_split_t2(net, b)) {
+                    if (launch_pack_tc_half_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, tc_tile_n(c.Cout),
+                                                    (cudaStream_t)stream))
+                        return 1;
+                } else if (net->precision == VST_CONV_F16X2 && c.tch) {
                     if (launch_pack_tch_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, c.Cout, terms,
                                                 (cudaStream_t)stream))
                         return 1;
