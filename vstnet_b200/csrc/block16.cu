@@ -67,11 +67,22 @@ __device__ __forceinline__ void tile_reflect(float4* t, int n, int pitch, int oy
     __syncthreads();
 }
 
-#define B16_FMA4(ACC, XV, WV)                 \
-    ACC[0] = fmaf(XV, WV.x, ACC[0]);          \
-    ACC[1] = fmaf(XV, WV.y, ACC[1]);          \
-    ACC[2] = fmaf(XV, WV.z, ACC[2]);          \
-    ACC[3] = fmaf(XV, WV.w, ACC[3]);
+// Packed fp32 FMA (Blackwell FFMA2): (d0, d1) += (a, a) * (b0, b1), IEEE fma per half — bit-identical to two
+// fmaf().  A three-register FFMA issues every other cycle per SM sub-partition (register-file read ports);
+// the packed form does two FMAs in the same issue slot, which is what reaches the fp32 peak.
+__device__ __forceinline__ void b16_fma2(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "mov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
+}
+#define B16_FMA4(ACC, XV, WV)                          \
+    b16_fma2(ACC[0], ACC[1], XV, WV.x, WV.y);          \
+    b16_fma2(ACC[2], ACC[3], XV, WV.z, WV.w);
 
 __device__ __forceinline__ void b16_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t ba = b16_smem_u32(bar);
@@ -98,23 +109,32 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(b3s + 16);   // [3] one per ring slot + weights
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TO, y0 = blockIdx.y * TO;
     const int H = a.H, W = a.W, Hp = H + 2, Wp = W + 2;
+    // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the input ring runs ahead across tile
+    // boundaries, so the next tile's first channel groups stream in while this tile's conv2 / conv3 run
+    const int n_tx = (W + TO - 1) / TO, n_tiles = n_tx * ((H + TO - 1) / TO);
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_items = 4 * my_tiles;                     // ring items: (tile, channel group)
+    const bool tr0 = a.trace && tid == 0 && blockIdx.x == gridDim.x / 2;
+    int trn = 0;
+#define B16_STAMP() do { if (tr) a.trace[trn++] = clock64(); } while (0)
 
     // ---- input halo tile (image rows y0-3 .. y0+30 = padded rows y0-2 ..), one channel group at a
     //      time through a 2-slot ring: one TMA bulk copy per row segment straight from the P4
     //      tensor, completion on the slot's mbarrier; group g+2 streams in while g+1 is computed.
-    const int shift = x0 < 2 ? 2 - x0 : 0;                 // tile columns left of the padded tensor
-    const uint32_t seg_bytes = (uint32_t)(XT - shift) * 16;
-    auto issue_group = [&](int g, int slot) {              // executed by all lanes of warp 0
+    auto issue_item = [&](int item) {                      // executed by all lanes of warp 0
+        const int tile = (int)blockIdx.x + (item >> 2) * (int)gridDim.x, g = item & 3, slot = item & 1;
+        const int tx0 = (tile % n_tx) * TO, ty0 = (tile / n_tx) * TO;
+        const int shift = tx0 < 2 ? 2 - tx0 : 0;           // tile columns left of the padded tensor
+        const uint32_t seg_bytes = (uint32_t)(XT - shift) * 16;
         if (lane == 0)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b16_smem_u32(&bars[slot])),
                          "r"(seg_bytes * XT) : "memory");
         __syncwarp();
         const float4* x4 = reinterpret_cast<const float4*>(a.x);
         for (int iy = lane; iy < XT; iy += 32) {
-            const int py = min(max(y0 - 2 + iy, 0), Hp - 1);
-            const float4* src = x4 + ((size_t)g * Hp + py) * Wp + (x0 - 2 + shift);
+            const int py = min(max(ty0 - 2 + iy, 0), Hp - 1);
+            const float4* src = x4 + ((size_t)g * Hp + py) * Wp + (tx0 - 2 + shift);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              b16_smem_u32(xs + slot * XG_F4 + iy * XT + shift)),
                          "l"(src), "r"(seg_bytes), "r"(b16_smem_u32(&bars[slot]))
@@ -136,21 +156,27 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
                              b16_smem_u32(ws)), "l"(a.w1), "r"((uint32_t)(W_FLOATS * 4)), "r"(b16_smem_u32(&bars[2]))
                          : "memory");
         }
-        issue_group(0, 0);
-        issue_group(1, 1);
+        issue_item(0);
+        issue_item(1);
     }
+    b16_wait(&bars[2], 0);                     // weights landed (once per CTA)
+
+  for (int k = 0; k < my_tiles; ++k) {
+    const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+    const int x0 = (tile % n_tx) * TO, y0 = (tile / n_tx) * TO;
+    const bool tr = tr0 && k == 1;
+    B16_STAMP();
     // ---- conv1 16 -> 4 on the 32x32 tile: t1(r, c) <-> image (y0-2+r, x0-2+c); warp = 8 rows, lane = col
     {
         float acc[8][4];
-        b16_wait(&bars[2], 0);                 // weights landed
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = b1s[c];
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-            const int slot = g & 1;
-            b16_wait(&bars[slot], (uint32_t)(g >> 1));
+            const int item = 4 * k + g, slot = item & 1;
+            b16_wait(&bars[slot], (uint32_t)((item >> 1) & 1));
 #pragma unroll 1
             for (int kx = 0; kx < 3; ++kx) {
                 float4 v[10];
@@ -173,10 +199,9 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
                     }
                 }
             }
-            if (g + 2 < 4) {
-                __syncthreads();                       // every warp is done reading this slot
-                if (warp == 0) issue_group(g + 2, slot);
-            }
+            B16_STAMP();
+            __syncthreads();                           // every warp is done reading this slot
+            if (warp == 0 && item + 2 < n_items) issue_item(item + 2);
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r)
@@ -185,6 +210,7 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
     }
     __syncthreads();
     tile_reflect(t1, T1, T1, y0 - 2, x0 - 2, H, W, tid);
+    B16_STAMP();
 
     // ---- conv2 4 -> 4 on the 30x30 tile: t2(r, c) <-> image (y0-1+r, x0-1+c); reads t1 rows r..r+2
     {
@@ -223,6 +249,7 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
     }
     __syncthreads();
     tile_reflect(t2, T2, T2_PITCH, y0 - 1, x0 - 1, H, W, tid);
+    B16_STAMP();
 
     // ---- conv3 4 -> 16 on the 28x28 tile, two passes of 8 output channels; warp = 7 rows
     const int x = x0 + lane;
@@ -268,6 +295,7 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
                 }
             }
         }
+        B16_STAMP();
         // ---- additive coupling + store (RevResNet.py:103, :110-111)
         if (xin) {
 #pragma unroll
@@ -284,7 +312,9 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
                 }
             }
         }
+        B16_STAMP();
     }
+  }   // tile loop
 }
 
 int launch_rev_block16(const Block16Args& a, cudaStream_t st) {
@@ -297,10 +327,13 @@ int launch_rev_block16(const Block16Args& a, cudaStream_t st) {
     VST_REQUIRE(a.b1 == a.w1 + 576 && a.w2 == a.b1 + 4 && a.b2 == a.w2 + 144 && a.w3 == a.b2 + 4 && a.b3 == a.w3 + 576 &&
                     ((uintptr_t)a.w1 & 15) == 0,
                 "rev_block16: the block's weight packs must be one contiguous 16-byte aligned run");
-    dim3 grid(cdiv(a.W, b16::TO), cdiv(a.H, b16::TO));
+    const int n_tiles = cdiv(a.W, b16::TO) * cdiv(a.H, b16::TO);
+    const int grid = std::min(n_tiles, 3 * num_sms());
+    Block16Args aa = a;
+    aa.trace = tc_trace_buffer(16, 4, st);
     const double px = (double)a.H * a.W;
     ProfScope prof(st, "rev_block16 (16>4>4>16)", 2.0 * 9 * (16 * 4 + 4 * 4 + 4 * 16) * px, 3.0 * 64.0 * px);
-    rev_block16_kernel<<<grid, 128, b16::SMEM, st>>>(a);
+    rev_block16_kernel<<<grid, 128, b16::SMEM, st>>>(aa);
     return check_launch("rev_block16");
 }
 

@@ -139,6 +139,7 @@ struct Block16Args {
     const float *w1, *b1, *w2, *b2, *w3, *b3;
     int H, W;
     int sub;             // 0: out = res + F(x)   1: out = res - F(x)
+    long long* trace;    // developer aid (VST_TC_TRACE="16,4"): clock64() stamps of one interior CTA
 };
 int launch_rev_block16(const Block16Args& a, cudaStream_t st);
 

@@ -167,7 +167,7 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
         a.w1 = packed + b.conv[0].pk_w; a.b1 = packed + b.conv[0].pk_b;
         a.w2 = packed + b.conv[1].pk_w; a.b2 = packed + b.conv[1].pk_b;
         a.w3 = packed + b.conv[2].pk_w; a.b3 = packed + b.conv[2].pk_b;
-        a.H = Hin; a.W = Win; a.sub = (epi == EPI_SUB) ? 1 : 0;
+        a.H = Hin; a.W = Win; a.sub = (epi == EPI_SUB) ? 1 : 0; a.trace = nullptr;
         return launch_rev_block16(a, st);
     }
     if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, st)) return 1;

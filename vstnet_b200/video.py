@@ -108,3 +108,59 @@ class VideoStylizer:
         host.copy_(o, non_blocking=True)
         st.synchronize()
         return host
+
+    @torch.no_grad()
+    def stylize_stream(self, frames, bgr=False):
+        """Pipelined end-to-end path for a sequence of HOST uint8 ``[H,W,3]`` frames (what cv2 / PIL deliver;
+        pinned memory makes the copies asynchronous).  Yields pinned uint8 ``[H,W,3]`` host tensors in order,
+        one frame behind the input: while frame i is stylized on the compute stream, frame i+1 is uploaded
+        and frame i-1 downloaded on two copy streams (double-buffered device and host staging).  Each yielded
+        tensor stays valid until two more frames have been yielded."""
+        dev = next(self.net.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        s_in, s_out = self._streams(dev)
+        din, dout, hout = [None, None], [None, None], [None, None]
+        ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_out = [torch.cuda.Event(), torch.cuda.Event()]
+        pending = None
+        for i, f in enumerate(frames):
+            b = i & 1
+            H, W = int(f.shape[0]), int(f.shape[1])
+            if din[b] is None or din[b].shape != f.shape:
+                din[b] = torch.empty(H, W, 3, dtype=torch.uint8, device=dev)
+                dout[b] = torch.empty(H, W, 3, dtype=torch.uint8, device=dev)
+                hout[b] = torch.empty(H, W, 3, dtype=torch.uint8).pin_memory()
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_done[b])            # frame i-2 no longer reads this input buffer
+                din[b].copy_(f.contiguous(), non_blocking=True)
+                ev_in[b].record(s_in)
+            main.wait_event(ev_in[b])
+            if i >= 2:
+                main.wait_event(ev_out[b])                 # frame i-2's download has left dout[b]
+            x = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
+            _lib.check(self._lib.vst_frame_u8_to_f32(din[b].data_ptr(), x.data_ptr(), H, W, int(bgr), main.cuda_stream),
+                       "vst_frame_u8_to_f32")
+            y = self.stylize(x)
+            _lib.check(self._lib.vst_frame_f32_to_u8(y.data_ptr(), dout[b].data_ptr(), H, W, int(bgr), main.cuda_stream),
+                       "vst_frame_f32_to_u8")
+            ev_done[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[b])
+                hout[b].copy_(dout[b], non_blocking=True)
+                ev_out[b].record(s_out)
+            if pending is not None:
+                ev_out[pending].synchronize()
+                yield hout[pending]
+            pending = b
+        if pending is not None:
+            ev_out[pending].synchronize()
+            yield hout[pending]
+
+    def _streams(self, dev):
+        k = str(dev)
+        if k not in self._pin:
+            self._pin[k] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        return self._pin[k]
+
