@@ -78,6 +78,42 @@ int launch_pack_tch_weights(const float* w, float* wp, int Cin, int Cout, int NC
     return check_launch("pack_tch_weights");
 }
 
+// The stride-2 conv of a transition block (RevResNet.py:79-81 with stride 2) as a stride-1 conv on the
+// SQUEEZED input: with xs[(dy*2+dx)*C + ci][h][w] = x[ci][2h+dy][2w+dx] (RevResNet.py:34-37),
+//     out(h,w) = sum_{ky,kx,ci} W[ky][kx][ci] x[ci][2h+ky-1][2w+kx-1]
+//              = sum over taps (ky',kx') in {0,1}^2 (offsets -1, 0) and squeezed channels (dy,dx,ci) of
+//                W[ky][kx][ci] xs[(dy,dx,ci)][h+ky'-1][w+kx'-1]   with  (ky',dy) -> ky: (0,1)->0, (1,0)->1, (1,1)->2
+// (same for x); every other (tap, sub-position) pair gets a zero weight.  4/9 of the MACs are on zeros, but
+// they run on the tensor cores in the kx-folded kernel above instead of on CUDA cores.  The reflection row
+// x[-1] = x[1] is xs[dy=1][h=0], i.e. the squeezed tensor needs its row 0 / column 0 REPLICATED into the
+// border (p4_replicate_topleft); the +1 taps have zero weights, so the other borders do not matter.
+// Output layout is that of pack_tch_weights_kernel with Cin' = 4C.
+__global__ void pack_tch_s2_weights_kernel(const float* __restrict__ w, __half* __restrict__ wp, int C, int Cout) {
+    const int NC = Cout, NP = 3 * NC, Cs = 4 * C;
+    const size_t total = (size_t)(Cs / 16) * 3 * 2 * NP * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int e = (int)(r % 8); r /= 8;
+        const int n = (int)(r % NP); r /= NP;
+        const int kh = (int)(r % 2); r /= 2;
+        const int kyp = (int)(r % 3); r /= 3;
+        const int chunk = (int)r;
+        const int kxp = n / NC, co = n - kxp * NC, cs = chunk * 16 + kh * 8 + e;
+        const int k = cs / C, ci = cs - k * C, dy = k >> 1, dx = k & 1;
+        const int ky = (kyp == 0 && dy == 1) ? 0 : (kyp == 1 ? 1 + dy : -1);
+        const int kx = (kxp == 0 && dx == 1) ? 0 : (kxp == 1 ? 1 + dx : -1);
+        const float v = (ky >= 0 && kx >= 0) ? w[((size_t)co * C + ci) * 9 + ky * 3 + kx] : 0.f;
+        wp[i] = __float2half_rn(v);
+    }
+}
+
+int launch_pack_tch_s2_weights(const float* w, float* wp, int C, int Cout, cudaStream_t st) {
+    const size_t total = (size_t)(4 * C / 16) * 3 * 2 * (3 * Cout) * 8;
+    pack_tch_s2_weights_kernel<<<(int)std::min<size_t>((total + 255) / 256, 4096), 256, 0, st>>>(
+        w, reinterpret_cast<__half*>(wp), C, Cout);
+    return check_launch("pack_tch_s2_weights");
+}
+
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), M=128, K=16
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {

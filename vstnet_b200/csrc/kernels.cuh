@@ -164,11 +164,14 @@ int launch_conv3x3_tcx(const ConvArgs& a, int terms, cudaStream_t st);
 bool tch_eligible(int Cin, int Cout, int stride);
 int launch_pack_tch_weights(const float* w, float* wp, int Cin, int Cout, int NC, int terms, cudaStream_t st);
 int launch_conv3x3_tch(const ConvArgs& a, int terms, cudaStream_t st);
+// stride-2 conv [Cout][C][3][3] as a stride-1 kx-folded conv on the squeezed (4C-channel) input
+int launch_pack_tch_s2_weights(const float* w, float* wp, int C, int Cout, cudaStream_t st);
 
 // layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
 int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st);   // NCHW -> P4
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st);           // P4 -> NCHW
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st);
+int launch_p4_replicate_topleft(float* t, int C, int H, int W, cudaStream_t st);
 int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Win, cudaStream_t st);
 int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st);
 int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, cudaStream_t st);

@@ -82,6 +82,28 @@ __global__ void depth_to_space_kernel(const float4* __restrict__ in, float4* __r
     }
 }
 
+// row -1 <- row 0 and column -1 <- column 0 (corner included) for every group: the border the squeezed-input
+// form of the stride-2 conv needs (conv_tch.cu, pack_tch_s2_weights_kernel).  O(perimeter).
+__global__ void p4_replicate_topleft_kernel(float4* __restrict__ t, int G, int H, int W) {
+    const int Wp = W + 2, per = (W + 1) + H;          // top row incl. corner, then the left column
+    const size_t total = (size_t)G * per;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / per), k = (int)(i - (size_t)g * per);
+        float4* p = t + (size_t)g * p4_plane_px(H, W);
+        if (k <= W) {                                  // padded row 0, padded columns 0..W  <- image row 0, column max(k-1, 0)
+            p[k] = p[(size_t)Wp + (k == 0 ? 1 : k)];
+        } else {                                       // padded column 0, padded rows 1..H  <- image column 0
+            const int r = k - W;
+            p[(size_t)r * Wp] = p[(size_t)r * Wp + 1];
+        }
+    }
+}
+int launch_p4_replicate_topleft(float* t, int C, int H, int W, cudaStream_t st) {
+    const size_t total = (size_t)(C / 4) * (W + 1 + H);
+    p4_replicate_topleft_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<float4*>(t), C / 4, H, W);
+    return check_launch("p4_replicate_topleft");
+}
+
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st) {
     VST_REQUIRE(C % 4 == 0, "space_to_depth: C must be a multiple of 4");
     const size_t total = (size_t)C * Hin * Win / 4;

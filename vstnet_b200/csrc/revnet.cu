@@ -20,6 +20,8 @@ struct ConvDesc {
     bool tc;              // eligible for the tcgen05 implicit-GEMM kernel
     bool tcx;             // ... in its kx-folded form (no coupling operand: conv1 / conv2 of a block)
     bool tch;             // ... kx-folded with fp16 split operands (precision f16x2)
+    bool s2tc;            // stride-2 conv runnable as a stride-1 tensor-core conv on the squeezed input (f16x2)
+    size_t pk_s2;         // float offset of that conv's remapped fp16 weight pack
     size_t pk_tc;         // float offset of the tensor-core weight pack (sized for hi+lo terms)
 };
 struct BlockDesc {
@@ -62,6 +64,9 @@ static void add_block(vst_revnet* n, std::vector<BlockDesc>& dst, int channel, i
         c.tch = k < 2 && tch_eligible(c.Cin, c.Cout, c.stride);
         c.pk_tc = n->packed_floats;
         if (c.tc) n->packed_floats += tc_packed_floats(c.Cin, c.Cout, tc_tile_n(c.Cout), 3);
+        c.s2tc = k == 0 && c.stride == 2 && tch_eligible(4 * c.Cin, c.Cout, 1);
+        c.pk_s2 = n->packed_floats;
+        if (c.s2tc) n->packed_floats += tc_packed_floats(4 * c.Cin, c.Cout, c.Cout, 1);
     }
     dst.push_back(b);
 }
@@ -156,8 +161,14 @@ static int run_conv(const vst_revnet* n, const ConvDesc& c, const float* packed,
 }
 
 // F(x) = conv3(relu(conv2(relu(conv1(x)))))  with the coupling fused into conv3's epilogue
+static bool block_s2tc(const vst_revnet* n, const BlockDesc& b) {
+    return n->precision == VST_CONV_F16X2 && b.stride == 2 && b.conv[0].s2tc;
+}
+
+// x_sq: for stride-2 blocks in f16x2 mode, squeeze(x) with its top/left border replicated (see conv_tch.cu)
 static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, const float* x, int Hin, int Win,
-                 const Workspace& ws, const float* res, float* out, int epi, cudaStream_t st) {
+                 const Workspace& ws, const float* res, float* out, int epi, cudaStream_t st,
+                 const float* x_sq = nullptr) {
     const int Ho = Hin / b.stride, Wo = Win / b.stride;
     if (b.stride == 1 && b.conv[0].Cin == 16 && b.conv[0].Cout == 4 && b.conv[2].Cout == 16 &&
         (epi == EPI_ADD || epi == EPI_SUB)) {
@@ -170,7 +181,13 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
         a.H = Hin; a.W = Win; a.sub = (epi == EPI_SUB) ? 1 : 0; a.trace = nullptr;
         return launch_rev_block16(a, st);
     }
-    if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, st)) return 1;
+    if (x_sq && block_s2tc(n, b)) {
+        const ConvDesc& c = b.conv[0];
+        ConvArgs a = conv_args(c, packed, x_sq, Ho, Wo, ws.T1, nullptr, EPI_RELU);
+        a.Cin = 4 * c.Cin; a.Hout = Ho; a.Wout = Wo;           // stride-1 conv on the squeezed tensor
+        a.w = packed + c.pk_s2;
+        if (launch_conv3x3_tch(a, 2, st)) return 1;
+    } else if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, st)) return 1;
     const bool split = block_split_t2(n, b);
     if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, st, split, false)) return 1;
     if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, st, false, split)) return 1;
@@ -191,11 +208,21 @@ static int forward_one(const vst_revnet* n, const float* packed, const float* x,
             if (run_F(n, b, packed, s1, h, w, ws, s0, s0, EPI_ADD, st)) return 1;
             std::swap(s0, s1);
         } else {
-            // y1 = F(s1) + squeeze(s0) -> spare ; new x1 = squeeze(s1) -> old s0 buffer
-            if (run_F(n, b, packed, s1, h, w, ws, s0, spare, EPI_ADD_SQZ, st)) return 1;
-            if (launch_space_to_depth(s1, s0, c, h, w, st)) return 1;
-            float* old_s1 = s1;
-            s1 = spare; spare = old_s1;      // (s0, s1) = (squeeze(x2), y1)
+            if (block_s2tc(n, b)) {
+                // new x1 = squeeze(s1) -> spare first: the stride-2 conv then runs on it (tensor cores);
+                // y1 = F(s1) + squeeze(s0) -> the now dead s1 buffer
+                if (launch_space_to_depth(s1, spare, c, h, w, st)) return 1;
+                if (launch_p4_replicate_topleft(spare, 4 * c, h / 2, w / 2, st)) return 1;
+                if (run_F(n, b, packed, s1, h, w, ws, s0, s1, EPI_ADD_SQZ, st, spare)) return 1;
+                float* old_s0 = s0;
+                s0 = spare; spare = old_s0;  // (s0, s1) = (squeeze(x2), y1)
+            } else {
+                // y1 = F(s1) + squeeze(s0) -> spare ; new x1 = squeeze(s1) -> old s0 buffer
+                if (run_F(n, b, packed, s1, h, w, ws, s0, spare, EPI_ADD_SQZ, st)) return 1;
+                if (launch_space_to_depth(s1, s0, c, h, w, st)) return 1;
+                float* old_s1 = s1;
+                s1 = spare; spare = old_s1;      // (s0, s1) = (squeeze(x2), y1)
+            }
             c *= 4; h /= 2; w /= 2;
         }
     }
@@ -231,7 +258,9 @@ static int inverse_one(const vst_revnet* n, const float* packed, const float* z,
         } else {
             // x2 = unsqueeze(s0) -> spare ; x1 = unsqueeze(s1 - F(x2)) -> old s0 buffer
             if (launch_depth_to_space(s0, spare, c / 4, h, w, st)) return 1;
-            if (run_F(n, b, packed, spare, 2 * h, 2 * w, ws, s1, s0, EPI_SUB_UNSQZ, st)) return 1;
+            const bool sq = block_s2tc(n, b);          // F's stride-2 conv reads the squeezed x2 (= s0) directly
+            if (sq && launch_p4_replicate_topleft(s0, c, h, w, st)) return 1;
+            if (run_F(n, b, packed, spare, 2 * h, 2 * w, ws, s1, s0, EPI_SUB_UNSQZ, st, sq ? s0 : nullptr)) return 1;
             float* old_s1 = s1;
             s1 = spare; spare = old_s1;      // (s0, s1) = (x1, x2)
             c /= 4; h *= 2; w *= 2;
@@ -309,6 +338,9 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
                                              c.CoutPad, (cudaStream_t)stream))
                     return 1;
                 const int terms = tc_terms(net->precision);
+                if (net->precision == VST_CONV_F16X2 && c.s2tc &&
+                    launch_pack_tch_s2_weights(raw + c.raw_w, pk + c.pk_s2, c.Cin, c.Cout, (cudaStream_t)stream))
+                    return 1;
                 if (k == 2 && block_split_t2(net, b)) {
                     if (launch_pack_tc_half_weights(raw + c.raw_w, pk + c.pk_tc, c.Cin, c.Cout, tc_tile_n(c.Cout),
                                                     (cudaStream_t)stream))

@@ -119,10 +119,10 @@ class VideoStylizer:
         dev = next(self.net.parameters()).device
         main = torch.cuda.current_stream(dev)
         s_in, s_out = self._streams(dev)
-        din, dout, hout = [None, None], [None, None], [None, None]
-        ev_in = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_done = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_out = [torch.cuda.Event(), torch.cuda.Event()]
+        st = self._pin.setdefault(("stream", str(dev)), {"din": [None, None], "dout": [None, None], "hout": [None, None],
+                                                         "ev": [[torch.cuda.Event() for _ in range(2)] for _ in range(3)]})
+        din, dout, hout = st["din"], st["dout"], st["hout"]          # staging survives across calls (pinning is slow)
+        ev_in, ev_done, ev_out = st["ev"]
         pending = None
         for i, f in enumerate(frames):
             b = i & 1
