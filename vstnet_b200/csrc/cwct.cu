@@ -11,6 +11,7 @@
 // fp32 products, fp64 cross-tile accumulation, pivot-shifted to avoid cancellation;
 // (2) factor — one CTA per label: covariance, Cholesky with the cumulative eps*I retry,
 // triangular solve, all in fp64 shared memory; (3) apply — label-indexed C x C transform.
+#include <stdlib.h>
 #include "kernels.cuh"
 
 namespace vst {
@@ -639,6 +640,10 @@ extern "C" int vst_cwct_stats(const float* feat, int C, long long n, const uint8
     const int sms = num_sms();
     ProfScope prof(st, C <= 32 ? "cwct_gram c32" : "cwct_gram c128", 2.0 * C * C * (double)n,
                    4.0 * C * (double)n + (labels ? (double)n : 0.0));
+    static int use_tc = -1;
+    if (use_tc < 0) { const char* e = getenv("VST_GRAM_TC"); use_tc = e ? atoi(e) : 1; }
+    if (!labels && use_tc && gram_tc_eligible(C, n) && (((uintptr_t)feat) & 15) == 0)
+        return launch_gram_tc(feat, sv.pivot, sv.count, sv.sum, sv.gram, C, n, st);     // tensor cores (gram_tc.cu)
     if (C <= 32) {
         int grid = labels ? sms * 3 : sms * 2;
         long long warps = (long long)grid * 8;

@@ -167,6 +167,11 @@ int launch_conv3x3_tch(const ConvArgs& a, int terms, cudaStream_t st);
 // stride-2 conv [Cout][C][3][3] as a stride-1 kx-folded conv on the squeezed (4C-channel) input
 int launch_pack_tch_s2_weights(const float* w, float* wp, int C, int Cout, cudaStream_t st);
 
+// tensor-core Gram + sums of an unmasked feature map (cWCT statistics), gram_tc.cu
+bool gram_tc_eligible(int C, long long n);
+int launch_gram_tc(const float* feat, const float* pivot, double* count, double* sum, double* gram, int C, long long n,
+                   cudaStream_t st);
+
 // layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
 int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st);   // NCHW -> P4
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st);           // P4 -> NCHW
