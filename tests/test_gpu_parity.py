@@ -265,6 +265,59 @@ def test_full_size_properties_1080p(dev):
     assert float((cWCT().interpolation(z, [zs], [1.0], 1.0) - z).abs().max()) <= 1e-5   # alpha_c = 1 keeps content
 
 
+def test_full_size_properties_cfg3_masked_1024(dev):
+    """BASELINE cfg3: photorealistic 1024x1024 with 8-label blocky masks (one label deliberately invalid).  Size-
+    independent properties of the per-label transform: every valid label's pixels take the style label's mean and
+    covariance, the invalid label's pixels are untouched, and the result is written into content_feat in place."""
+    from vstnet_b200 import cWCT
+    net = build_net("photo", 0, 7).to(dev)
+    gen = torch.Generator(device=dev)
+    x = torch.rand(1, 3, 1024, 1024, device=dev, generator=gen.manual_seed(11))
+    s = torch.rand(1, 3, 1024, 1024, device=dev, generator=gen.manual_seed(12))
+    cm = blocky_mask(1024, 1024, 2, 4, [0, 1, 2, 3, 4, 5, 6, 7])
+    sm = blocky_mask(1024, 1024, 4, 2, [3, 1, 0, 2, 7, 6, 4, 4])          # label 5 absent from the style: invalid
+    zc, zs = net(x), net(s)
+    zc0 = zc.clone()
+    out = cWCT().transfer(zc, zs, cm, sm)
+    assert out.data_ptr() == zc.data_ptr()
+    cmt, smt = torch.from_numpy(cm[0]).to(dev), torch.from_numpy(sm[0]).to(dev)
+    for l in range(8):
+        sel = (cmt == l)
+        a = out[0][:, sel].double()
+        if l == 5:
+            assert torch.equal(out[0][:, sel], zc0[0][:, sel]), "invalid label must keep the content features"
+            continue
+        b = zs[0][:, smt == l].double()
+        assert float((a.mean(1) - b.mean(1)).abs().max()) <= 2e-5
+        assert float((torch.cov(a) - torch.cov(b)).abs().max()) <= 2e-4 * float(torch.cov(b).abs().max())
+    y = net(out, forward=False)
+    assert bool(torch.isfinite(y).all())
+
+
+def test_full_size_properties_cfg5_art_4096(dev):
+    """BASELINE cfg5: artistic 4096x4096 (latent [1,128,2048,2048], 2.1 GB).  Round trip at fp32 level, the
+    interpolated transfer moves the statistics (1-alpha) of the way, alpha_c = 1 returns the content."""
+    from vstnet_b200 import cWCT
+    net = build_net("art", 0, 7).to(dev)
+    gen = torch.Generator(device=dev)
+    x = torch.rand(1, 3, 4096, 4096, device=dev, generator=gen.manual_seed(21))
+    z = net(x)
+    assert tuple(z.shape) == (1, 128, 2048, 2048)
+    assert float((net.inverse(z) - x).abs().max()) <= 2e-6
+    s = torch.rand(1, 3, 1024, 1024, device=dev, generator=gen.manual_seed(22))
+    zs = net(s)
+    zcs = cWCT().transfer(z, zs)
+    a, b = zcs[0].reshape(128, -1), zs[0].reshape(128, -1).double()
+    assert float((a.double().mean(1) - b.mean(1)).abs().max()) <= 2e-5
+    sub = a[:, ::7].double()                                   # covariance on a 1/7 pixel subsample (memory)
+    cb = torch.cov(b)
+    assert float((torch.cov(sub) - cb).abs().max()) <= 2e-2 * float(cb.abs().max())
+    del zcs, a, sub
+    assert float((cWCT().interpolation(z, [zs], [1.0], 1.0) - z).abs().max()) <= 2e-5
+    y = net(cWCT().interpolation(z, [zs], [1.0], 0.5), forward=False)
+    assert tuple(y.shape) == (1, 3, 4096, 4096) and bool(torch.isfinite(y).all())
+
+
 def test_frame_conversion(dev):
     import ctypes
     from vstnet_b200 import _lib

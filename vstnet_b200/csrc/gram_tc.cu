@@ -210,7 +210,9 @@ static int launch_gram_tc_cfg(const GramTcArgs& a0, cudaStream_t st) {
     return check_launch("cwct_gram_tc");
 }
 
-bool gram_tc_eligible(int C, long long n) { return C >= 1 && C <= 128 && n % 4 == 0; }
+// small maps stay on the CUDA-core kernels: exact fp32 products (a two-term tf32 split carries 22 bits), and a
+// persistent tensor-core pipeline has nothing to amortise there
+bool gram_tc_eligible(int C, long long n) { return C >= 1 && C <= 128 && n % 4 == 0 && n >= 16384; }
 
 // sums and Gram of the pivot-shifted features into zero-initialised fp64 buffers (one label)
 int launch_gram_tc(const float* feat, const float* pivot, double* count, double* sum, double* gram, int C, long long n,
