@@ -5,8 +5,9 @@ Workload (BASELINE.json configs[3], the one `metric` is quoted on): photorealist
 random-init RevResNet (seed 0), synthetic frames, the style image encoded and its cWCT statistics
 hoisted once (rank 0) and NCCL-broadcast; every rank then stylizes its own frames.  A *step* is
 one 1920x1080 frame per rank: encode -> cWCT stats/factor/apply -> decode.  `value` is whole-job
-frames/s with frames resident in HBM; `e2e` is the same through `VideoStylizer.stylize_host`
-with HOST buffers (pinned fp32 frame H2D + uint8 result D2H inside the timed region).
+frames/s with frames resident in HBM; `e2e` is the same through `VideoStylizer.stylize_stream`
+with HOST buffers (pinned uint8 HWC frame H2D + uint8 result D2H inside the timed region, pipelined).
+`images` (N = 1 only) adds ms per image for the other BASELINE configs (cfg1/2/3/5).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nproc-per-node N ... bench.py --gpus N ...
@@ -158,6 +159,78 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
+# the other BASELINE configs (single images): reported as extras, "ms per image" = 2 encodes + cWCT + decode
+# ----------------------------------------------------------------------------------------------
+def image_configs_ms(dev, precision, with_cpu):
+    import numpy as np
+    import torch
+    from vstnet_b200 import RevResNet, cWCT
+
+    def blocky(h, w, gy, gx, perm):
+        m = np.zeros((h, w), np.uint8)
+        ys, xs = np.linspace(0, h, gy + 1).astype(int), np.linspace(0, w, gx + 1).astype(int)
+        for i in range(gy):
+            for j in range(gx):
+                m[ys[i]:ys[i + 1], xs[j]:xs[j + 1]] = perm[i * gx + j]
+        return m[None]
+
+    out = {}
+    nets = {}
+    for name, mode, size, alpha, masked in (("cfg1_photo_512", "photo", 512, None, False),
+                                            ("cfg2_art_1024_alpha0.5", "art", 1024, 0.5, False),
+                                            ("cfg3_photo_1024_masked8", "photo", 1024, None, True),
+                                            ("cfg5_art_4096", "art", 4096, None, False)):
+        if mode not in nets:
+            torch.manual_seed(0)
+            kw = dict(hidden_dim=16, sp_steps=2) if mode == "photo" else dict(hidden_dim=64, sp_steps=1)
+            nets[mode] = RevResNet(**kw, precision=precision).to(dev).eval()
+        net, cw = nets[mode], cWCT()
+        g = torch.Generator(device=dev).manual_seed(7)
+        c = torch.rand(1, 3, size, size, device=dev, generator=g)
+        s = torch.rand(1, 3, size, size, device=dev, generator=g)
+        cm = torch.from_numpy(blocky(size, size, 2, 4, [0, 1, 2, 3, 4, 5, 6, 7])).to(dev) if masked else None
+        sm = torch.from_numpy(blocky(size, size, 4, 2, [3, 1, 0, 2, 7, 6, 4, 5])).to(dev) if masked else None
+
+        def run():
+            zc, zs = net(c), net(s)
+            if masked:
+                zcs = cw.transfer(zc, zs, cm, sm)
+            elif alpha is not None:
+                zcs = cw.interpolation(zc, [zs], [1.0], alpha)
+            else:
+                zcs = cw.transfer(zc, zs)
+            return net(zcs, forward=False)
+
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        a.record()
+        for _ in range(reps):
+            run()
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = {"gpu_ms": round(a.elapsed_time(b) / reps, 3)}
+        del c, s
+        torch.cuda.empty_cache()
+    if with_cpu:                      # the reference's own CPU-runnable case (configs[0]) on the host cores
+        from oracle import vst_oracle as O
+        torch.manual_seed(0)
+        net = RevResNet(hidden_dim=16, sp_steps=2)
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        gc = torch.Generator().manual_seed(7)
+        c, s = torch.rand(1, 3, 512, 512, generator=gc), torch.rand(1, 3, 512, 512, generator=gc)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            y = O.revnet_inverse(sd, O.cwct_transfer(O.revnet_forward(sd, c), O.revnet_forward(sd, s)))
+            float(y[0, 0, 0, 0])
+            out["cfg1_photo_512"]["cpu_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+            out["cfg1_photo_512"]["cpu_cores"] = os.cpu_count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -304,6 +377,12 @@ def run_ours(args):
         v, sample, _, _ = bounded_cpu_sample(25.0, 1, 1, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
+    images = None
+    if world == 1 and not args.no_images:
+        del frames, host_frames
+        torch.cuda.empty_cache()
+        images = image_configs_ms(dev, args.precision, not args.no_cpu)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -319,6 +398,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "useful_conv_tflops": 2 * CONV_FLOP_PER_PX * H * W * world * K / (ms / 1e3) / 1e12,
         "profile_pass_ms_per_step": ms_prof / K,
+        "images": images,
         "kernels": kernels[:12],
     }
     print(json.dumps(line), flush=True)
@@ -334,6 +414,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f16x2", help="conv arithmetic: f16x2 (default) | tf32x2 | tf32x3 | tf32 | fp32")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-images", action="store_true", help="skip the single-image configs (cfg1/2/3/5 extras)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps is None:
