@@ -143,6 +143,14 @@ struct Block16Args {
 };
 int launch_rev_block16(const Block16Args& a, cudaStream_t st);
 
+// the same for C = 16 / 64 as ONE row-streaming tcgen05 kernel (precision f16x2), block_tc.cu
+bool block_tc_eligible(int C, int mult);
+size_t block_tc_pack_floats(int C);
+int launch_pack_block_tc(int C, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                         const float* b3, float* pk, cudaStream_t st);
+int launch_rev_block_tc(int C, const float* x, const float* res, float* out, const float* wpack, int H, int W, int sub,
+                        cudaStream_t st);
+
 // tensor-core (tcgen05) path, conv_tc.cu
 bool tc_eligible(int Cin, int Cout, int stride);
 int tc_tile_n(int Cout);

@@ -9,6 +9,7 @@
 // so split()/merge() (RevResNet.py:8-16) are pointer bookkeeping, not copies.
 #include <vector>
 #include <new>
+#include <stdlib.h>
 #include "kernels.cuh"
 
 namespace vst {
@@ -27,6 +28,8 @@ struct ConvDesc {
 struct BlockDesc {
     int channel, stride;
     ConvDesc conv[3];
+    bool btc;             // whole block runnable as one row-streaming tensor-core kernel (block_tc.cu, f16x2)
+    size_t pk_blk;        // float offset of that kernel's block pack (16-byte aligned)
 };
 
 }  // namespace vst
@@ -68,7 +71,20 @@ static void add_block(vst_revnet* n, std::vector<BlockDesc>& dst, int channel, i
         c.pk_s2 = n->packed_floats;
         if (c.s2tc) n->packed_floats += tc_packed_floats(4 * c.Cin, c.Cout, c.Cout, 1);
     }
+    b.btc = stride == 1 && block_tc_eligible(channel, n->cfg.mult);
+    b.pk_blk = align_up(n->packed_floats, 4);
+    if (b.btc) n->packed_floats = b.pk_blk + block_tc_pack_floats(channel);
     dst.push_back(b);
+}
+
+// VST_BLOCK_TC (developer knob): bit 0 = fused tensor-core block for C = 16, bit 1 = for C = 64; default both
+static int block_tc_mask() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VST_BLOCK_TC"); v = e ? atoi(e) : 3; }
+    return v;
+}
+static bool block_fused_tc(const vst_revnet* n, const BlockDesc& b) {
+    return n->precision == VST_CONV_F16X2 && b.btc && (block_tc_mask() & (b.channel == 16 ? 1 : 2));
 }
 
 struct Shape { int c, h, w; };
@@ -170,6 +186,8 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
                  const Workspace& ws, const float* res, float* out, int epi, cudaStream_t st,
                  const float* x_sq = nullptr) {
     const int Ho = Hin / b.stride, Wo = Win / b.stride;
+    if (block_fused_tc(n, b) && (epi == EPI_ADD || epi == EPI_SUB) && Win >= 4)
+        return launch_rev_block_tc(b.channel, x, res, out, packed + b.pk_blk, Hin, Win, epi == EPI_SUB ? 1 : 0, st);
     if (b.stride == 1 && b.conv[0].Cin == 16 && b.conv[0].Cout == 4 && b.conv[2].Cout == 16 &&
         (epi == EPI_ADD || epi == EPI_SUB)) {
         // full-resolution stage: the whole block in one fused CUDA-core kernel (block16.cu)
@@ -331,7 +349,12 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
     VST_REQUIRE(((uintptr_t)packed & 15) == 0, "packed buffer must be 16-byte aligned");
     float* pk = (float*)packed;
     for (const std::vector<BlockDesc>* lst : {&net->stack, &net->cr})
-        for (const BlockDesc& b : *lst)
+        for (const BlockDesc& b : *lst) {
+            if (net->precision == VST_CONV_F16X2 && b.btc &&
+                launch_pack_block_tc(b.channel, raw + b.conv[0].raw_w, raw + b.conv[0].raw_b, raw + b.conv[1].raw_w,
+                                     raw + b.conv[1].raw_b, raw + b.conv[2].raw_w, raw + b.conv[2].raw_b, pk + b.pk_blk,
+                                     (cudaStream_t)stream))
+                return 1;
             for (int k = 0; k < 3; ++k) {
                 const ConvDesc& c = b.conv[k];
                 if (launch_pack_conv_weights(raw + c.raw_w, raw + c.raw_b, pk + c.pk_w, pk + c.pk_b, c.Cin, c.Cout,
@@ -358,6 +381,7 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
                                                   (cudaStream_t)stream))
                     return 1;
             }
+        }
     return 0;
 }
 
