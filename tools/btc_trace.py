@@ -24,6 +24,7 @@ def show(role, name, per, labels, rows=range(10, 16)):
     # steady-state period
     s = r[per * 10::per][:40]; s = s[s > 0]
     if len(s) > 2: print("  period: %.0f cycles/row" % ((s[-1] - s[0]) / (len(s) - 1)))
-show(0, "issuer", 6, ["begin", "x_full ok", "conv1 issued", "conv2 go", "conv3 go", "end"])
+show(0, "issuer", 6, ["begin", "conv3 go", "conv3 done", "conv2 go", "conv1 go", "end"])
 show(1, "converter", 3, ["begin", "x_empty ok", "arrived"])
 show(4, "E3", 4, ["begin", "acc ok", "barrier", "end"])
+show(5, "E3 block 0 detail", 8, ["tmem_ld done", "published", "barrier", "math done", "stored"])

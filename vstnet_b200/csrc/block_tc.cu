@@ -35,13 +35,16 @@ struct BtcCfg {
     static constexpr int N1 = (3 * M < 16) ? 16 : 3 * M; // UMMA N of conv1 / conv2: (kx, co), padded to 16
     static constexpr int N3 = 3 * C;                     // UMMA N of conv3
     static constexpr int TT = (M == 4) ? 1 : 2;          // operand terms of a t row (M = 4: hi|lo packed into K)
+    static constexpr int NB = (C == 16) ? 2 : 1;         // 128-pixel blocks per CTA step (amortises the per-step barrier traffic)
     static constexpr int PW = 128, XO = 122;
     static constexpr int CHUNK = PW * 16;                // one 8-half K chunk of one row: [pixel][16 B]
     static constexpr int XT = (C / 8) * CHUNK;           // one term of an x row: [C/8 chunks][pixel][16 B]
-    static constexpr int X_SLOT = 2 * XT;
+    static constexpr int X_BLK = 2 * XT;
+    static constexpr int X_SLOT = NB * X_BLK;
     static constexpr int NX = 3;
     static constexpr int T_TERM = 2 * CHUNK;
-    static constexpr int T_SLOT = TT * T_TERM;
+    static constexpr int T_BLK = TT * T_TERM;
+    static constexpr int T_SLOT = NB * T_BLK;
     static constexpr int NT = 4;
     static constexpr int W1_BYTES = 3 * KS * 2 * N1 * 16;    // [ky][k step][chunk][n][8 halfs]
     static constexpr int W2_BYTES = 3 * 2 * N1 * 16;         // [ky][chunk][n][8 halfs]
@@ -49,7 +52,7 @@ struct BtcCfg {
     static constexpr int BIAS_FLOATS = 2 * M + C;            // b1 | b2 | b3
     static constexpr int WPACK_BYTES = W1_BYTES + W2_BYTES + W3_BYTES + ((BIAS_FLOATS * 4 + 15) / 16) * 16;
     static constexpr int NA1 = 4, NA2 = 2, NA3 = (C == 64) ? 1 : 2;   // powers of two
-    static constexpr int A1 = 0, A2 = A1 + NA1 * N1, A3 = A2 + NA2 * N1, ACOLS = A3 + NA3 * N3;
+    static constexpr int A1 = 0, A2 = A1 + NA1 * N1, A3 = A2 + NA2 * N1, ACOLS_BLK = A3 + NA3 * N3, ACOLS = NB * ACOLS_BLK;
     static constexpr int TMEM_COLS = ACOLS <= 128 ? 128 : ACOLS <= 256 ? 256 : 512;
     static constexpr int EXCH_FLOATS = 2 * 2 * (4 * 2 * M) + 2 * (4 * 2 * C);   // E1, E2 (double-buffered) + E3
     static constexpr int AUX_BYTES = 512 + EXCH_FLOATS * 4;
@@ -213,9 +216,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     using Cfg = BtcCfg<C>;
     constexpr int M = Cfg::M, N = Cfg::N1;
     const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
-    const int m = q * 32 + lane, x = g.x0 - 3 + m;
-    const bool own = (x >= 0) && (x < g.W);
-    const bool mir_l = (x == 1) && (m >= 2), mir_r = (x == g.W - 2) && (m + 2 < Cfg::PW);
+    const int m = q * 32 + lane;
     float bs[M];
 #pragma unroll
     for (int c = 0; c < M; ++c) bs[c] = btc_lds(g.bias + 4 * c);
@@ -223,64 +224,74 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     const uint32_t ex_l = g.exch + (uint32_t)(((q > 0 ? q - 1 : 0) * 2 + 0) * M * 4);          // left warp's lane 31, kx = 0
     const uint32_t ex_r = g.exch + (uint32_t)(((q < 3 ? q + 1 : 3) * 2 + 1) * M * 4);          // right warp's lane 0, kx = 2
     const uint32_t trow = g.tacc + ((uint32_t)(q * 32) << 16);
+    uint32_t par = 0;
 #pragma unroll 1
     for (int l = 0; l < g.rows; ++l) {
         const int st = l & 3, sa = l & (g.nacc - 1);
-        const uint32_t pa = (uint32_t)((l >> g.nacc_log2) & 1);
-        const uint32_t par = (uint32_t)(l & 1) * (4 * 2 * M * 4);
-        mbar_wait_a(g.acc_full + 8 * sa, pa);
+        mbar_wait_a(g.acc_full + 8 * sa, (uint32_t)((l >> g.nacc_log2) & 1));
         tc_fence_after();
-        float d[3 * M < 16 ? 16 : 3 * M];
-        if (M == 4) {
-            tmem_ld<16>(trow + (uint32_t)(sa * N), d);
-        } else {
+#pragma unroll 1
+        for (int blk = 0; blk < Cfg::NB; ++blk, par ^= (uint32_t)(4 * 2 * M * 4)) {
+            const int x = g.x0 + blk * Cfg::XO - 3 + m;
+            const bool own = (x >= 0) && (x < g.W);
+            const bool mir_l = (x == 1) && (m >= 2), mir_r = (x == g.W - 2) && (m + 2 < Cfg::PW);
+            uint32_t du[3 * M < 16 ? 16 : 3 * M];
+            if (M == 4) {
+                tmem_ld16_nowait(trow + (uint32_t)(blk * Cfg::ACOLS_BLK + sa * N), du);
+            } else {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) tmem_ld<16>(trow + (uint32_t)(sa * N + kx * 16), d + kx * 16);
-        }
-        tc_fence_before();
-        if (lane == 31 || lane == 0) {
+                for (int kx = 0; kx < 3; ++kx) tmem_ld16_nowait(trow + (uint32_t)(blk * Cfg::ACOLS_BLK + sa * N + kx * 16), du + kx * 16);
+            }
+            tmem_ld_wait();
+            tmem_ld_fence_regs<(3 * M < 16 ? 16 : 3 * M)>(du);
+            float d[3 * M < 16 ? 16 : 3 * M];
 #pragma unroll
-            for (int c = 0; c < M; ++c) btc_sts(ex_pub + par + 4 * c, lane == 0 ? d[2 * M + c] : d[c]);
-        }
-        named_barrier(g.bar_id, 128);
-        // neighbour-warp partial sums: warp-uniform addresses (broadcast loads), all issued before any use
-        float el[M], er[M];
+            for (int c = 0; c < (3 * M < 16 ? 16 : 3 * M); ++c) d[c] = __uint_as_float(du[c]);
+            if (lane == 31 || lane == 0) {
 #pragma unroll
-        for (int c = 0; c < M; c += 4) {
-            const float4 a4 = btc_lds128(ex_l + par + 4 * c), b4 = btc_lds128(ex_r + par + 4 * c);
-            el[c] = a4.x; el[c + 1] = a4.y; el[c + 2] = a4.z; el[c + 3] = a4.w;
-            er[c] = b4.x; er[c + 1] = b4.y; er[c + 2] = b4.z; er[c + 3] = b4.w;
-        }
-        float o[M];
+                for (int c = 0; c < M; ++c) btc_sts(ex_pub + par + 4 * c, lane == 0 ? d[2 * M + c] : d[c]);
+            }
+            named_barrier(g.bar_id, 128);
+            // neighbour-warp partial sums: warp-uniform addresses (broadcast loads), all issued before any use
+            float el[M], er[M];
 #pragma unroll
-        for (int c = 0; c < M; ++c) {
-            const float ls = __shfl_up_sync(0xffffffffu, d[c], 1);
-            const float rs = __shfl_down_sync(0xffffffffu, d[2 * M + c], 1);
-            const float lv = (lane == 0) ? el[c] : ls;
-            const float rv = (lane == 31) ? er[c] : rs;
-            o[c] = fmaxf(((lv + d[M + c]) + rv) * (1.0f / VST_HALF_SCALE) + bs[c], 0.f) * VST_HALF_SCALE;
-        }
-        mbar_wait_a(g.t_empty + 8 * st, (uint32_t)(((l >> 2) & 1) ^ 1));
-        const uint32_t slot = g.tring + (uint32_t)(st * Cfg::T_SLOT + m * 16);
-        if (M == 4) {
-            const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const uint4 v = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23),
-                                       btc_pack_half2(o[0] - f01.x, o[1] - f01.y), btc_pack_half2(o[2] - f23.x, o[3] - f23.y));
-            if (own) btc_sts128(slot, v);
-            if (mir_l) btc_sts128(slot - 32, v);
-            if (mir_r) btc_sts128(slot + 32, v);
-        } else {
+            for (int c = 0; c < M; c += 4) {
+                const float4 a4 = btc_lds128(ex_l + par + 4 * c), b4 = btc_lds128(ex_r + par + 4 * c);
+                el[c] = a4.x; el[c + 1] = a4.y; el[c + 2] = a4.z; el[c + 3] = a4.w;
+                er[c] = b4.x; er[c + 1] = b4.y; er[c + 2] = b4.z; er[c + 3] = b4.w;
+            }
+            float o[M];
 #pragma unroll
-            for (int k = 0; k < M / 8; ++k) {
-                uint4 hv, lv;
-                btc_split8(o + 8 * k, hv, lv);
-                const uint32_t ph = slot + k * Cfg::CHUNK, pl = ph + Cfg::T_TERM;      // term 0 (hi) / term 1 (lo), chunk k
-                if (own) { btc_sts128(ph, hv); btc_sts128(pl, lv); }
-                if (mir_l) { btc_sts128(ph - 32, hv); btc_sts128(pl - 32, lv); }
-                if (mir_r) { btc_sts128(ph + 32, hv); btc_sts128(pl + 32, lv); }
+            for (int c = 0; c < M; ++c) {
+                const float ls = __shfl_up_sync(0xffffffffu, d[c], 1);
+                const float rs = __shfl_down_sync(0xffffffffu, d[2 * M + c], 1);
+                const float lv = (lane == 0) ? el[c] : ls;
+                const float rv = (lane == 31) ? er[c] : rs;
+                o[c] = fmaxf(((lv + d[M + c]) + rv) * (1.0f / VST_HALF_SCALE) + bs[c], 0.f) * VST_HALF_SCALE;
+            }
+            if (blk == 0) mbar_wait_a(g.t_empty + 8 * st, (uint32_t)(((l >> 2) & 1) ^ 1));
+            const uint32_t slot = g.tring + (uint32_t)(st * Cfg::T_SLOT + blk * Cfg::T_BLK + m * 16);
+            if (M == 4) {
+                const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const uint4 v = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23),
+                                           btc_pack_half2(o[0] - f01.x, o[1] - f01.y), btc_pack_half2(o[2] - f23.x, o[3] - f23.y));
+                if (own) btc_sts128(slot, v);
+                if (mir_l) btc_sts128(slot - 32, v);
+                if (mir_r) btc_sts128(slot + 32, v);
+            } else {
+#pragma unroll
+                for (int k = 0; k < M / 8; ++k) {
+                    uint4 hv, lv;
+                    btc_split8(o + 8 * k, hv, lv);
+                    const uint32_t ph = slot + k * Cfg::CHUNK, pl = ph + Cfg::T_TERM;      // term 0 (hi) / term 1 (lo), chunk k
+                    if (own) { btc_sts128(ph, hv); btc_sts128(pl, lv); }
+                    if (mir_l) { btc_sts128(ph - 32, hv); btc_sts128(pl - 32, lv); }
+                    if (mir_r) { btc_sts128(ph + 32, hv); btc_sts128(pl + 32, lv); }
+                }
             }
         }
+        tc_fence_before();
         fence_proxy_async();
         mbar_arrive_a(g.t_full + 8 * st);
     }
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
     BtcSeg sg;
     {
         const int sx = blockIdx.x % a.n_strips, sy = blockIdx.x / a.n_strips;
-        sg.x0 = sx * Cfg::XO;
+        sg.x0 = sx * (Cfg::NB * Cfg::XO);
         sg.ya = sy * a.rows_per_seg;
         sg.yb = min(H, sg.ya + a.rows_per_seg);
         if (sg.ya >= H) return;
@@ -412,8 +423,11 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                         const uint64_t ad = dT2 + (uint64_t)(st * (Cfg::T_SLOT >> 4));
                         const uint64_t bd = dW3 + (uint64_t)((ky * 2 * N3 * 16) >> 4);
 #pragma unroll
-                        for (int t = 0; t < TT; ++t)
-                            if (el) btc_umma_f16(dcol, ad + (uint64_t)((t * Cfg::T_TERM) >> 4), bd, IDESC3, ky > 0 || t > 0);
+                        for (int blk = 0; blk < Cfg::NB; ++blk)
+#pragma unroll
+                            for (int t = 0; t < TT; ++t)
+                                if (el) btc_umma_f16(dcol + blk * Cfg::ACOLS_BLK, ad + (uint64_t)((blk * Cfg::T_BLK + t * Cfg::T_TERM) >> 4), bd,
+                                                     IDESC3, ky > 0 || t > 0);
                     }
                     if (el) umma_commit_a(b3_full + 8 * sa);
                     if (el && y - 1 >= sg.t2a) umma_commit_a(bt2_empty + 8 * ((y - 1 - sg.t2a) & 3));
@@ -436,8 +450,11 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                         const uint64_t ad = dT1 + (uint64_t)(st * (Cfg::T_SLOT >> 4));
                         const uint64_t bd = dW2 + (uint64_t)((ky * 2 * N1 * 16) >> 4);
 #pragma unroll
-                        for (int t = 0; t < TT; ++t)
-                            if (el) btc_umma_f16(dcol, ad + (uint64_t)((t * Cfg::T_TERM) >> 4), bd, IDESC1, ky > 0 || t > 0);
+                        for (int blk = 0; blk < Cfg::NB; ++blk)
+#pragma unroll
+                            for (int t = 0; t < TT; ++t)
+                                if (el) btc_umma_f16(dcol + blk * Cfg::ACOLS_BLK, ad + (uint64_t)((blk * Cfg::T_BLK + t * Cfg::T_TERM) >> 4), bd,
+                                                     IDESC1, ky > 0 || t > 0);
                     }
                     if (el) umma_commit_a(b2_full + 8 * sa);
                     if (el && i - 1 >= sg.t1a) umma_commit_a(bt1_empty + 8 * ((i - 1 - sg.t1a) & 3));
@@ -457,8 +474,12 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
 #pragma unroll
                             for (int ks = 0; ks < KS; ++ks) {
                                 const uint64_t bd = dW1 + (uint64_t)(((ky * KS + ks) * 2 * N1 * 16) >> 4);
-                                if (el) btc_umma_f16(dcol, dXs + (uint64_t)((ks * 2 * Cfg::CHUNK) >> 4), bd, IDESC1, ky > 0 || ks > 0);
-                                if (el) btc_umma_f16(dcol, dXs + (uint64_t)((Cfg::XT + ks * 2 * Cfg::CHUNK) >> 4), bd, IDESC1, true);
+#pragma unroll
+                                for (int blk = 0; blk < Cfg::NB; ++blk) {
+                                    const uint64_t ax = dXs + (uint64_t)((blk * Cfg::X_BLK + ks * 2 * Cfg::CHUNK) >> 4);
+                                    if (el) btc_umma_f16(dcol + blk * Cfg::ACOLS_BLK, ax, bd, IDESC1, ky > 0 || ks > 0);
+                                    if (el) btc_umma_f16(dcol + blk * Cfg::ACOLS_BLK, ax + (uint64_t)(Cfg::XT >> 4), bd, IDESC1, true);
+                                }
                             }
                             if (ky == 2 && el) umma_commit_a(b1_full + 8 * sa);
                         }
@@ -473,46 +494,54 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
         __syncwarp();
     } else if (warp >= 16) {
         // ================= converters: fp32 P4 rows (global / L2) -> fp16 hi | lo operand rows =================
-        const int m = tid - 16 * 32;                                  // staged pixel
+        const int m = tid - 16 * 32;                                  // staged pixel (of every block)
+        constexpr int NB = Cfg::NB;
         const int pc0 = max(sg.x0 - 2, 0);
-        const int pc = min(max(sg.x0 - 2 + m, 0), Wp - 1);            // padded column (clamped: garbage pixels only)
+        int pcb[NB];                                                  // padded column per block (clamped: garbage pixels only)
+#pragma unroll
+        for (int blk = 0; blk < NB; ++blk) pcb[blk] = min(max(sg.x0 + blk * Cfg::XO - 2 + m, 0), Wp - 1);
         const size_t plane = (size_t)Hp * Wp;
         const float4* in4 = reinterpret_cast<const float4*>(a.x);
         const uint32_t bx_full = smem_u32(x_full), bx_empty = smem_u32(x_empty);
         int s = 0;
         uint32_t pe = 1;
         constexpr int GB = G < 8 ? G : 8;                             // groups per batch of loads in flight
-        constexpr int NBATCH = G / GB;
-        // software pipeline: batch b+1 (possibly of the next row) is requested before batch b is converted
+        constexpr int NBATCH = G / GB, ITEMS = NB * NBATCH;           // item = (block, batch) of one row
+        // software pipeline: the next item (possibly of the next row) is requested before the current one is converted
         float4 v[GB];
         {
-            const float4* src = in4 + (size_t)(sg.xa + 1) * Wp + pc;
+            const float4* src = in4 + (size_t)(sg.xa + 1) * Wp + pcb[0];
 #pragma unroll
             for (int g = 0; g < GB; ++g) v[g] = __ldg(src + (size_t)g * plane);
         }
 #pragma unroll 1
         for (int rx = sg.xa; rx <= sg.xb; ++rx) {
-            if (m < G && rx + BTC_PREFETCH_ROWS <= sg.xb)
-                l2_prefetch(in4 + (size_t)m * plane + (size_t)(rx + 1 + BTC_PREFETCH_ROWS) * Wp + pc0, Cfg::CHUNK);
+            if (m < G && rx + BTC_PREFETCH_ROWS <= sg.xb) {
+#pragma unroll
+                for (int blk = 0; blk < NB; ++blk)
+                    l2_prefetch(in4 + (size_t)m * plane + (size_t)(rx + 1 + BTC_PREFETCH_ROWS) * Wp + min(pc0 + blk * Cfg::PW, Wp - 1), Cfg::CHUNK);
+            }
             if (m == 0) BTC_TRACE(1, 3 * (rx - sg.xa));
             mbar_wait_a(bx_empty + 8 * s, pe);
             if (m == 0) BTC_TRACE(1, 3 * (rx - sg.xa) + 1);
-            const uint32_t hi = smem_u32(xring) + (uint32_t)(s * Cfg::X_SLOT + m * 16);
-#pragma unroll 1
-            for (int b = 0; b < NBATCH; ++b) {
+            const uint32_t hi0 = smem_u32(xring) + (uint32_t)(s * Cfg::X_SLOT + m * 16);
+#pragma unroll
+            for (int it = 0; it < ITEMS; ++it) {
+                const int blk = it / NBATCH, b = it % NBATCH;
                 float xs[4 * GB];
 #pragma unroll
                 for (int g = 0; g < GB; ++g) {
                     xs[4 * g] = v[g].x * VST_HALF_SCALE; xs[4 * g + 1] = v[g].y * VST_HALF_SCALE;
                     xs[4 * g + 2] = v[g].z * VST_HALF_SCALE; xs[4 * g + 3] = v[g].w * VST_HALF_SCALE;
                 }
-                {   // next batch: same row, or batch 0 of the next row (clamped at the end: a harmless re-read)
-                    const int nb = (b + 1 == NBATCH) ? 0 : b + 1;
-                    const int nrow = min((b + 1 == NBATCH) ? rx + 1 : rx, sg.xb);
-                    const float4* src = in4 + (size_t)(nb * GB) * plane + (size_t)(nrow + 1) * Wp + pc;
+                {   // next item: same row, or item 0 of the next row (clamped at the end: a harmless re-read)
+                    const int nit = (it + 1 == ITEMS) ? 0 : it + 1;
+                    const int nrow = min((it + 1 == ITEMS) ? rx + 1 : rx, sg.xb);
+                    const float4* src = in4 + (size_t)((nit % NBATCH) * GB) * plane + (size_t)(nrow + 1) * Wp + pcb[nit / NBATCH];
 #pragma unroll
                     for (int g = 0; g < GB; ++g) v[g] = __ldg(src + (size_t)g * plane);
                 }
+                const uint32_t hi = hi0 + blk * Cfg::X_BLK;
 #pragma unroll
                 for (int k = 0; k < GB / 2; ++k) {
                     uint4 hv, lv;
@@ -546,12 +575,12 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
         btc_mid_epilogue<C>(g);
     } else {
         // ================= E3: acc3 -> kx fold, bias, coupling with res -> global P4 (+ reflection border) =================
-        constexpr int CPT = Cfg::CPT, CH = Cfg::CH;
+        constexpr int CPT = Cfg::CPT, CH = Cfg::CH, NB = Cfg::NB;
         const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
-        const int x = sg.x0 - 3 + m;
-        const bool xin = (m >= 3) && (m < 3 + Cfg::XO) && (x < W);
+        const int xb0 = sg.x0 - 3 + m;                                       // image column of this thread in block 0
+        const bool min_ok = (m >= 3) && (m < 3 + Cfg::XO);
         const size_t plane = (size_t)Hp * Wp;
-        const float4* resp = reinterpret_cast<const float4*>(a.res) + (size_t)(half * (CPT / 4)) * plane + (x + 1);
+        const float4* resp = reinterpret_cast<const float4*>(a.res) + (size_t)(half * (CPT / 4)) * plane + (xb0 + 1);
         float4* outp = reinterpret_cast<float4*>(a.out) + (size_t)(half * (CPT / 4)) * plane;
         const float sgn = a.sub ? -1.f : 1.f;
         mbar_wait_a(smem_u32(w_bar), 0u);
@@ -561,73 +590,111 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
         const int l_off = ((q > 0 ? q - 1 : 0) * 2 + 0) * C, r_off = ((q < 3 ? q + 1 : 3) * 2 + 1) * C;
         const uint32_t b3_full = smem_u32(a3_full), b3_empty = smem_u32(a3_empty);
         const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A3 + half * CPT;
+        int par = 0;                                                         // exchange buffer parity, toggles per (row, block)
 #pragma unroll 1
         for (int y = sg.ya; y < sg.yb; ++y) {
             const int ly = y - sg.ya, sa = ly & (NA3 - 1);
             if (tid == 0) BTC_TRACE(4, 4 * ly);
             if (tid < G && y + BTC_PREFETCH_ROWS < sg.yb)
                 l2_prefetch(reinterpret_cast<const float4*>(a.res) + (size_t)tid * plane + (size_t)(y + 1 + BTC_PREFETCH_ROWS) * Wp + sg.x0 + 1,
-                            (uint32_t)(min(Cfg::XO, W - sg.x0) * 16));
-            float4 r[CH / 4];                            // coupling operand (single-pass path: requested before the wait)
+                            (uint32_t)(max(min(NB * Cfg::XO, W - sg.x0), 1) * 16));
+            const size_t rowoff = (size_t)(y + 1) * Wp;
             if (CPT == CH) {
+                // ---- all of this thread's couts fit in registers: one pass per block
+                float4 r[NB][CH / 4];                    // coupling operand, requested before the accumulator wait
 #pragma unroll
-                for (int j = 0; j < CH / 4; ++j)
-                    r[j] = xin ? resp[(size_t)j * plane + (size_t)(y + 1) * Wp] : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            mbar_wait_a(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
-            tc_fence_after();
-            if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
-            const uint32_t trow = trow0 + sa * N3;
-            float* ex = ex_base + (ly & 1) * (4 * 2 * C);
-            if (CPT == CH) {
-                // ---- all of this thread's couts fit in registers: one pass
-                float v0[CH], v1[CH], v2[CH];
-                tmem_ld<CH>(trow + 0 * C, v0);
-                tmem_ld<CH>(trow + 1 * C, v1);
-                tmem_ld<CH>(trow + 2 * C, v2);
-                tc_fence_before();
-                mbar_arrive_a(b3_empty + 8 * sa);
-                if (lane == 31 || lane == 0) {
+                for (int blk = 0; blk < NB; ++blk)
 #pragma unroll
-                    for (int i = 0; i < CH; i += 4)
-                        *reinterpret_cast<float4*>(ex + pub_off + i) = lane == 0 ? make_float4(v2[i], v2[i + 1], v2[i + 2], v2[i + 3])
-                                                                                 : make_float4(v0[i], v0[i + 1], v0[i + 2], v0[i + 3]);
-                }
-                named_barrier(3 + half, 128);
-                if (tid == 0) BTC_TRACE(4, 4 * ly + 2);
-                float el[CH], er[CH], bb[CH];
+                    for (int j = 0; j < CH / 4; ++j)
+                        r[blk][j] = (min_ok && xb0 + blk * Cfg::XO < W) ? resp[(size_t)j * plane + rowoff + blk * Cfg::XO]
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                mbar_wait_a(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
+                tc_fence_after();
+                if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
 #pragma unroll
-                for (int i = 0; i < CH; i += 4) {       // warp-uniform addresses (broadcast), all issued before any use
-                    const float4 a4 = *reinterpret_cast<const float4*>(ex + l_off + i);
-                    const float4 c4 = *reinterpret_cast<const float4*>(ex + r_off + i);
-                    const float4 d4 = *reinterpret_cast<const float4*>(b3p + i);
-                    el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
-                    er[i] = c4.x; er[i + 1] = c4.y; er[i + 2] = c4.z; er[i + 3] = c4.w;
-                    bb[i] = d4.x; bb[i + 1] = d4.y; bb[i + 2] = d4.z; bb[i + 3] = d4.w;
-                }
+                for (int blk = 0; blk < NB; ++blk, par ^= 1) {
+                    const int x = xb0 + blk * Cfg::XO;
+                    const bool xin = min_ok && (x < W);
+                    const uint32_t trow = trow0 + blk * Cfg::ACOLS_BLK + sa * N3;
+                    float* ex = ex_base + par * (4 * 2 * C);
+                    uint32_t u0[CH], u1[CH], u2[CH];
+                    tmem_ld8_nowait(trow + 0 * C, u0);
+                    tmem_ld8_nowait(trow + 1 * C, u1);
+                    tmem_ld8_nowait(trow + 2 * C, u2);
+                    tmem_ld_wait();
+                    tmem_ld_fence_regs<CH>(u0); tmem_ld_fence_regs<CH>(u1); tmem_ld_fence_regs<CH>(u2);
+                    float v0[CH], v1[CH], v2[CH];
 #pragma unroll
-                for (int i = 0; i < CH; ++i) {
-                    const float ls = __shfl_up_sync(0xffffffffu, v0[i], 1);
-                    const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
-                    const float lv = (lane == 0) ? el[i] : ls;
-                    const float rv = (lane == 31) ? er[i] : rs;
-                    v1[i] = sgn * (((lv + v1[i]) + rv) * (1.0f / VST_HALF_SCALE) + bb[i]);
-                }
-                if (xin) {
-#pragma unroll
-                    for (int j = 0; j < CH / 4; ++j) {
-                        float4 o;
-                        o.x = r[j].x + v1[4 * j]; o.y = r[j].y + v1[4 * j + 1]; o.z = r[j].z + v1[4 * j + 2]; o.w = r[j].w + v1[4 * j + 3];
-                        p4_store(outp + (size_t)j * plane, H, W, y, x, o);
+                    for (int i = 0; i < CH; ++i) { v0[i] = __uint_as_float(u0[i]); v1[i] = __uint_as_float(u1[i]); v2[i] = __uint_as_float(u2[i]); }
+                    if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly);
+                    if (blk == NB - 1) {
+                        tc_fence_before();
+                        mbar_arrive_a(b3_empty + 8 * sa);
                     }
+                    if (lane == 31 || lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < CH; i += 4)
+                            *reinterpret_cast<float4*>(ex + pub_off + i) = lane == 0 ? make_float4(v2[i], v2[i + 1], v2[i + 2], v2[i + 3])
+                                                                                     : make_float4(v0[i], v0[i + 1], v0[i + 2], v0[i + 3]);
+                    }
+                    if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 1);
+                    named_barrier(3 + half, 128);
+                    if (tid == 0) BTC_TRACE(4, 4 * ly + 2);
+                    if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 2);
+                    float el[CH], er[CH], bb[CH];
+#pragma unroll
+                    for (int i = 0; i < CH; i += 4) {       // warp-uniform addresses (broadcast), all issued before any use
+                        const float4 a4 = *reinterpret_cast<const float4*>(ex + l_off + i);
+                        const float4 c4 = *reinterpret_cast<const float4*>(ex + r_off + i);
+                        const float4 d4 = *reinterpret_cast<const float4*>(b3p + i);
+                        el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
+                        er[i] = c4.x; er[i + 1] = c4.y; er[i + 2] = c4.z; er[i + 3] = c4.w;
+                        bb[i] = d4.x; bb[i + 1] = d4.y; bb[i + 2] = d4.z; bb[i + 3] = d4.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const float ls = __shfl_up_sync(0xffffffffu, v0[i], 1);
+                        const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
+                        const float lv = (lane == 0) ? el[i] : ls;
+                        const float rv = (lane == 31) ? er[i] : rs;
+                        v1[i] = sgn * (((lv + v1[i]) + rv) * (1.0f / VST_HALF_SCALE) + bb[i]);
+                    }
+                    if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 3);
+                    if (xin) {
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j) {
+                            const float4 rr = r[blk][j];
+                            float4 o;
+                            o.x = rr.x + v1[4 * j]; o.y = rr.y + v1[4 * j + 1]; o.z = rr.z + v1[4 * j + 2]; o.w = rr.w + v1[4 * j + 3];
+                            p4_store(outp + (size_t)j * plane, H, W, y, x, o);
+                        }
+                    }
+                    if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 4);
                 }
             } else {
+                static_assert(CPT == CH || NB == 1, "the chunked E3 path handles one block per step");
+                const int x = xb0;
+                const bool xin = min_ok && (x < W);
+                float4 r[CH / 4], rn[CH / 4];            // coupling operand of the current / next cout chunk, requested early
+#pragma unroll
+                for (int j = 0; j < CH / 4; ++j) r[j] = xin ? resp[(size_t)j * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
+                mbar_wait_a(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
+                tc_fence_after();
+                if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
+                const uint32_t trow = trow0 + sa * N3;
+                float* ex = ex_base + par * (4 * 2 * C);
+                par ^= 1;
                 // ---- phase 1: publish the partial sums the neighbouring warp needs (lane 31's kx=0, lane 0's kx=2)
 #pragma unroll
                 for (int c0 = 0; c0 < CPT; c0 += CH) {
+                    uint32_t u0[CH], u2[CH];
+                    tmem_ld8_nowait(trow + (uint32_t)(0 * C + c0), u0);
+                    tmem_ld8_nowait(trow + (uint32_t)(2 * C + c0), u2);
+                    tmem_ld_wait();
+                    tmem_ld_fence_regs<CH>(u0); tmem_ld_fence_regs<CH>(u2);
                     float v0[CH], v2[CH];
-                    tmem_ld<CH>(trow + (uint32_t)(0 * C + c0), v0);
-                    tmem_ld<CH>(trow + (uint32_t)(2 * C + c0), v2);
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) { v0[i] = __uint_as_float(u0[i]); v2[i] = __uint_as_float(u2[i]); }
                     if (lane == 31 || lane == 0) {
 #pragma unroll
                         for (int i = 0; i < CH; i += 4)
@@ -641,9 +708,11 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                 // ---- phase 2
 #pragma unroll
                 for (int c0 = 0; c0 < CPT; c0 += CH) {
+                    if (c0 + CH < CPT) {
 #pragma unroll
-                    for (int j = 0; j < CH / 4; ++j)
-                        r[j] = xin ? resp[(size_t)(c0 / 4 + j) * plane + (size_t)(y + 1) * Wp] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < CH / 4; ++j)
+                            rn[j] = xin ? resp[(size_t)((c0 + CH) / 4 + j) * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     float el[CH], er[CH], bb[CH];
 #pragma unroll
                     for (int i = 0; i < CH; i += 4) {
@@ -654,10 +723,15 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                         er[i] = c4.x; er[i + 1] = c4.y; er[i + 2] = c4.z; er[i + 3] = c4.w;
                         bb[i] = d4.x; bb[i + 1] = d4.y; bb[i + 2] = d4.z; bb[i + 3] = d4.w;
                     }
+                    uint32_t u0[CH], u1[CH], u2[CH];
+                    tmem_ld8_nowait(trow + (uint32_t)(0 * C + c0), u0);
+                    tmem_ld8_nowait(trow + (uint32_t)(1 * C + c0), u1);
+                    tmem_ld8_nowait(trow + (uint32_t)(2 * C + c0), u2);
+                    tmem_ld_wait();
+                    tmem_ld_fence_regs<CH>(u0); tmem_ld_fence_regs<CH>(u1); tmem_ld_fence_regs<CH>(u2);
                     float v0[CH], v1[CH], v2[CH];
-                    tmem_ld<CH>(trow + (uint32_t)(0 * C + c0), v0);
-                    tmem_ld<CH>(trow + (uint32_t)(1 * C + c0), v1);
-                    tmem_ld<CH>(trow + (uint32_t)(2 * C + c0), v2);
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) { v0[i] = __uint_as_float(u0[i]); v1[i] = __uint_as_float(u1[i]); v2[i] = __uint_as_float(u2[i]); }
                     if (c0 + CH >= CPT) {           // last TMEM read of this accumulator
                         tc_fence_before();
                         mbar_arrive_a(b3_empty + 8 * sa);
@@ -679,6 +753,8 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                             p4_store(outp + (size_t)(c0 / 4 + j) * plane, H, W, y, x, o);
                         }
                     }
+#pragma unroll
+                    for (int j = 0; j < CH / 4; ++j) r[j] = rn[j];
                 }
             }
             if (tid == 0) BTC_TRACE(4, 4 * ly + 3);
@@ -702,7 +778,7 @@ static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
         VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
     }
-    a.n_strips = cdiv(a.W, Cfg::XO);
+    a.n_strips = cdiv(a.W, Cfg::NB * Cfg::XO);
     int nseg = std::max(1, num_sms() / a.n_strips);
     a.rows_per_seg = cdiv(a.H, nseg);
     if (a.rows_per_seg < 8) a.rows_per_seg = std::min(8, a.H);

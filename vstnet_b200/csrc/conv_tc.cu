@@ -300,6 +300,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                 mbar_wait(&acc_full[b], (tcount >> 1) & 1);
                 tc_fence_after();
                 if (tid == 0) TC_TRACE(6, tcount);
+                // TMEM -> registers is software-pipelined: the load of chunk t+1 is in flight while chunk t is
+                // combined and stored (a tcgen05.ld takes ~200 cycles while the tensor pipe is busy)
+                constexpr int NCHK = NG * 4 / CH;
+                uint32_t ub[2][CH];
+                tmem_ld_nowait<CH>(trow, ub[0]);                       // warp-collective
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (r < rows) {                                    // warp-uniform
@@ -307,8 +312,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                         const bool up = (y == 1), dn = (y == H - 2);   // row also feeds border row -1 / H
 #pragma unroll
                         for (int c0 = 0; c0 < NG * 4; c0 += CH) {
+                            constexpr int dummy = 0; (void)dummy;
+                            const int t = r * NCHK + c0 / CH;
+                            tmem_ld_wait();
+                            tmem_ld_fence_regs<CH>(ub[t & 1]);
                             float v[CH];
-                            tmem_ld<CH>(trow + (uint32_t)(r * N + c0), v);       // warp-collective
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(ub[t & 1][i]);
+                            if (t + 1 < R * NCHK && (c0 + CH < NG * 4 || r + 1 < rows))
+                                tmem_ld_nowait<CH>(trow + (uint32_t)(((t + 1) / NCHK) * N + ((t + 1) % NCHK) * CH), ub[(t + 1) & 1]);
                             if (xin) {
 #pragma unroll
                                 for (int jj = 0; jj < CH / 4; ++jj) {

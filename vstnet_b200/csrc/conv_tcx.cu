@@ -241,8 +241,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
 #pragma unroll 1
                 for (int c0 = 0; c0 < HC; c0 += CH) {
                     float v0[CH], v2[CH];
-                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0);
-                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
+                    tmem_ld2<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0, trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
                     if (lane == 31) {
 #pragma unroll
                         for (int i = 0; i < CH; ++i) ex[((r * 4 + q) * 2 + 0) * NC + half * HC + c0 + i] = v0[i];
@@ -264,9 +263,8 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
 #pragma unroll 1
                 for (int c0 = 0; c0 < HC; c0 += CH) {
                     float v0[CH], v1[CH], v2[CH];
-                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0);
-                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 1 * NC + c0), v1);
-                    tmem_ld<CH>(trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
+                    tmem_ld3<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0, trow + (uint32_t)(r * NP + 1 * NC + c0), v1,
+                                 trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
                     if (tid == 0 && tcount == 1) TCX_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 0);
                     const int cb = half * HC + c0;                  // first cout of this chunk (within the tile)
                     const float* exl = ex + ((r * 4 + (q > 0 ? q - 1 : 0)) * 2 + 0) * NC + cb;   // left neighbour warp, lane 31

@@ -149,6 +149,55 @@ __device__ __forceinline__ void tmem_ld<64>(uint32_t taddr, float* v) {
     tmem_ld<32>(taddr + 32, v + 32);
 }
 
+
+// the same without the trailing wait: issue several loads back to back, then tmem_ld_wait() once (a tcgen05.ld
+// takes ~200+ cycles while the tensor pipe is busy; waiting after each one serialises that latency)
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// pins the consumers of registers written by a tcgen05.ld *_nowait behind the tmem_ld_wait() that precedes this call
+// (volatile asm statements keep their order; an ordinary use could otherwise be scheduled above the wait)
+template <int N>
+__device__ __forceinline__ void tmem_ld_fence_regs(uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+r"(r[i]));
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t* r) {
+    if (NC == 8) tmem_ld8_nowait(taddr, r);
+    else { static_assert(NC == 8 || NC == 16, "8 or 16 columns"); tmem_ld16_nowait(taddr, r); }
+}
+// 2 or 3 column blocks of NC columns each: loads issued back to back, ONE wait
+template <int NC>
+__device__ __forceinline__ void tmem_ld3(uint32_t t0, float* v0, uint32_t t1, float* v1, uint32_t t2, float* v2) {
+    uint32_t u0[NC], u1[NC], u2[NC];
+    tmem_ld_nowait<NC>(t0, u0); tmem_ld_nowait<NC>(t1, u1); tmem_ld_nowait<NC>(t2, u2);
+    tmem_ld_wait();
+    tmem_ld_fence_regs<NC>(u0); tmem_ld_fence_regs<NC>(u1); tmem_ld_fence_regs<NC>(u2);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { v0[i] = __uint_as_float(u0[i]); v1[i] = __uint_as_float(u1[i]); v2[i] = __uint_as_float(u2[i]); }
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld2(uint32_t t0, float* v0, uint32_t t1, float* v1) {
+    uint32_t u0[NC], u1[NC];
+    tmem_ld_nowait<NC>(t0, u0); tmem_ld_nowait<NC>(t1, u1);
+    tmem_ld_wait();
+    tmem_ld_fence_regs<NC>(u0); tmem_ld_fence_regs<NC>(u1);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { v0[i] = __uint_as_float(u0[i]); v1[i] = __uint_as_float(u1[i]); }
+}
+
 // shared -> global bulk store (TMA engine); completion tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
