@@ -28,3 +28,7 @@ show(0, "issuer", 6, ["begin", "conv3 go", "conv3 done", "conv2 go", "conv1 go",
 show(1, "converter", 3, ["begin", "x_empty ok", "arrived"])
 show(4, "E3", 4, ["begin", "acc ok", "barrier", "end"])
 show(5, "E3 block 0 detail", 8, ["tmem_ld done", "published", "barrier", "math done", "stored"])
+print("== per-role accounting: total cycles in the row loop, cycles inside barrier waits, steps")
+for role, name in [(0, "issuer"), (3, "converter"), (1, "E1"), (2, "E2"), (4, "E3")]:
+    tot, wt, n = a[7][role * 8: role * 8 + 3]
+    if n > 0: print("  %-10s total %8d  wait %8d  steps %4d  ->  busy %.0f cycles/step, wait %.0f cycles/step" % (name, tot, wt, n, (tot - wt) / n, wt / n))

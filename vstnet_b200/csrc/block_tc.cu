@@ -81,6 +81,16 @@ struct BlockTcArgs {
 #else
 #define BTC_TRACE(role, idx) do { } while (0)
 #endif
+// wait accounting (tracing builds): per role, cycles spent inside barrier waits vs in the whole row loop
+#ifdef BTC_TRACING
+#define BTC_WAIT(addr, par) do { const long long _t = clock64(); mbar_wait_a(addr, par); btc_wait_cycles += clock64() - _t; } while (0)
+#define BTC_ACC_BEGIN() long long btc_wait_cycles = 0; const long long btc_t0 = clock64()
+#define BTC_ACC_END(tr, role, steps) do { if (tr) { (tr)[7 * 4096 + (role) * 8] = clock64() - btc_t0; (tr)[7 * 4096 + (role) * 8 + 1] = btc_wait_cycles; (tr)[7 * 4096 + (role) * 8 + 2] = (steps); } } while (0)
+#else
+#define BTC_WAIT(addr, par) mbar_wait_a(addr, par)
+#define BTC_ACC_BEGIN() do { } while (0)
+#define BTC_ACC_END(tr, role, steps) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------
 // weights: raw OIHW fp32 of the three convs -> one contiguous block pack (fp16 operands + fp32 biases)
@@ -210,6 +220,7 @@ struct BtcMidArgs {
     uint32_t tring, t_full, t_empty;
     uint32_t bias, exch;
     int nacc, nacc_log2, rows, bar_id, x0, W;
+    long long* trace;              // tracing builds: wait accounting of this role (nullptr otherwise)
 };
 template <int C>
 static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
@@ -225,10 +236,11 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     const uint32_t ex_r = g.exch + (uint32_t)(((q < 3 ? q + 1 : 3) * 2 + 1) * M * 4);          // right warp's lane 0, kx = 2
     const uint32_t trow = g.tacc + ((uint32_t)(q * 32) << 16);
     uint32_t par = 0;
+    BTC_ACC_BEGIN();
 #pragma unroll 1
     for (int l = 0; l < g.rows; ++l) {
         const int st = l & 3, sa = l & (g.nacc - 1);
-        mbar_wait_a(g.acc_full + 8 * sa, (uint32_t)((l >> g.nacc_log2) & 1));
+        BTC_WAIT(g.acc_full + 8 * sa, (uint32_t)((l >> g.nacc_log2) & 1));
         tc_fence_after();
 #pragma unroll 1
         for (int blk = 0; blk < Cfg::NB; ++blk, par ^= (uint32_t)(4 * 2 * M * 4)) {
@@ -269,7 +281,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
                 const float rv = (lane == 31) ? er[c] : rs;
                 o[c] = fmaxf(((lv + d[M + c]) + rv) * (1.0f / VST_HALF_SCALE) + bs[c], 0.f) * VST_HALF_SCALE;
             }
-            if (blk == 0) mbar_wait_a(g.t_empty + 8 * st, (uint32_t)(((l >> 2) & 1) ^ 1));
+            if (blk == 0) BTC_WAIT(g.t_empty + 8 * st, (uint32_t)(((l >> 2) & 1) ^ 1));
             const uint32_t slot = g.tring + (uint32_t)(st * Cfg::T_SLOT + blk * Cfg::T_BLK + m * 16);
             if (M == 4) {
                 const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
@@ -295,6 +307,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
         fence_proxy_async();
         mbar_arrive_a(g.t_full + 8 * st);
     }
+    if (m == 0) BTC_ACC_END(g.trace, g.bar_id, g.rows);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -401,6 +414,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
             //                                           before E2 published t2 row rx-6]
             //   wait x row rx     -> conv1(rx)         [starts t1 row rx+1 in the acc1 slot of row rx-3, drained before
             //                                           E1 published t1 row rx-3]
+            BTC_ACC_BEGIN();
 #pragma unroll 1
             for (int rx = sg.xa;; ++rx) {
                 const bool el = btc_elect_one();
@@ -408,12 +422,12 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                 // ---- conv3: out row y from t2 rows mir(y-1), y, mir(y+1)
                 {
                     const int r2 = rx - 6 - sg.t2a;
-                    if (r2 >= 0 && rx - 6 <= sg.t2b) mbar_wait_a(bt2_full + 8 * (r2 & 3), (uint32_t)((r2 >> 2) & 1));
+                    if (r2 >= 0 && rx - 6 <= sg.t2b) BTC_WAIT(bt2_full + 8 * (r2 & 3), (uint32_t)((r2 >> 2) & 1));
                 }
                 const int y = rx - 7;
                 if (y >= sg.ya && y < sg.yb) {
                     const int ly = y - sg.ya, sa = ly & (NA3 - 1);
-                    mbar_wait_a(b3_empty + 8 * sa, (uint32_t)(((ly >> (NA3 - 1)) & 1) ^ 1));
+                    BTC_WAIT(b3_empty + 8 * sa, (uint32_t)(((ly >> (NA3 - 1)) & 1) ^ 1));
                     tc_fence_after();
                     BTC_TRACE(0, 6 * (rx - sg.xa) + 1);
                     const uint32_t dcol = tmem_base + Cfg::A3 + sa * N3;
@@ -436,7 +450,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                 // ---- conv2: t2 row i from t1 rows mir(i-1), i, mir(i+1)
                 {
                     const int r1 = rx - 3 - sg.t1a;
-                    if (r1 >= 0 && rx - 3 <= sg.t1b) mbar_wait_a(bt1_full + 8 * (r1 & 3), (uint32_t)((r1 >> 2) & 1));
+                    if (r1 >= 0 && rx - 3 <= sg.t1b) BTC_WAIT(bt1_full + 8 * (r1 & 3), (uint32_t)((r1 >> 2) & 1));
                 }
                 const int i = rx - 4;
                 if (i >= sg.t2a && i <= sg.t2b) {
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                 }
                 // ---- conv1: x row rx -> t1 rows rx-1 (ky=2, completes it), rx (ky=1), rx+1 (ky=0, starts it)
                 if (rx <= sg.xb) {
-                    mbar_wait_a(bx_full + 8 * sx, px);
+                    BTC_WAIT(bx_full + 8 * sx, px);
                     tc_fence_after();
                     BTC_TRACE(0, 6 * (rx - sg.xa) + 4);
                     const uint64_t dXs = dX + (uint64_t)(sx * (Cfg::X_SLOT >> 4));
@@ -490,6 +504,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                 BTC_TRACE(0, 6 * (rx - sg.xa) + 5);
                 if (y >= sg.yb - 1) break;
             }
+            if (lane == 0) BTC_ACC_END((a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr, 0, sg.yb + 7 - sg.xa);
         }
         __syncwarp();
     } else if (warp >= 16) {
@@ -514,6 +529,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
 #pragma unroll
             for (int g = 0; g < GB; ++g) v[g] = __ldg(src + (size_t)g * plane);
         }
+        BTC_ACC_BEGIN();
 #pragma unroll 1
         for (int rx = sg.xa; rx <= sg.xb; ++rx) {
             if (m < G && rx + BTC_PREFETCH_ROWS <= sg.xb) {
@@ -522,7 +538,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     l2_prefetch(in4 + (size_t)m * plane + (size_t)(rx + 1 + BTC_PREFETCH_ROWS) * Wp + min(pc0 + blk * Cfg::PW, Wp - 1), Cfg::CHUNK);
             }
             if (m == 0) BTC_TRACE(1, 3 * (rx - sg.xa));
-            mbar_wait_a(bx_empty + 8 * s, pe);
+            BTC_WAIT(bx_empty + 8 * s, pe);
             if (m == 0) BTC_TRACE(1, 3 * (rx - sg.xa) + 1);
             const uint32_t hi0 = smem_u32(xring) + (uint32_t)(s * Cfg::X_SLOT + m * 16);
 #pragma unroll
@@ -555,6 +571,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
             if (m == 0) BTC_TRACE(1, 3 * (rx - sg.xa) + 2);
             if (++s == NX) { s = 0; pe ^= 1u; }
         }
+        if (m == 0) BTC_ACC_END((a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr, 3, sg.xb - sg.xa + 1);
     } else if (warp >= 8) {
         // ================= E1 (warps 8-11) / E2 (warps 12-15) =================
         mbar_wait_a(smem_u32(w_bar), 0u);
@@ -572,6 +589,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
         g.rows = second ? sg.t2b - sg.t2a + 1 : sg.t1b - sg.t1a + 1;
         g.bar_id = second ? 2 : 1;
         g.x0 = sg.x0; g.W = W;
+        g.trace = (a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr;
         btc_mid_epilogue<C>(g);
     } else {
         // ================= E3: acc3 -> kx fold, bias, coupling with res -> global P4 (+ reflection border) =================
@@ -584,13 +602,19 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
         float4* outp = reinterpret_cast<float4*>(a.out) + (size_t)(half * (CPT / 4)) * plane;
         const float sgn = a.sub ? -1.f : 1.f;
         mbar_wait_a(smem_u32(w_bar), 0u);
-        const float* b3p = bias_s + 2 * M + half * CPT;                      // this thread's couts
-        float* ex_base = exch3 + half * CPT;
-        const int pub_off = (q * 2 + (lane == 0 ? 1 : 0)) * C;               // where lane 31 / lane 0 publish
-        const int l_off = ((q > 0 ? q - 1 : 0) * 2 + 0) * C, r_off = ((q < 3 ? q + 1 : 3) * 2 + 1) * C;
+        // shared-memory objects as 32-bit shared addresses (explicit ld/st.shared: no generic-address path)
+        const uint32_t b3p = smem_u32(bias_s + 2 * M + half * CPT);          // this thread's couts
+        const uint32_t ex_base = smem_u32(exch3 + half * CPT);
+        const uint32_t pub_off = (uint32_t)((q * 2 + (lane == 0 ? 1 : 0)) * C * 4);   // where lane 31 / lane 0 publish
+        const uint32_t l_off = (uint32_t)(((q > 0 ? q - 1 : 0) * 2 + 0) * C * 4), r_off = (uint32_t)(((q < 3 ? q + 1 : 3) * 2 + 1) * C * 4);
         const uint32_t b3_full = smem_u32(a3_full), b3_empty = smem_u32(a3_empty);
         const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A3 + half * CPT;
         int par = 0;                                                         // exchange buffer parity, toggles per (row, block)
+        float4 rs[CH / 4], rn[CH / 4];                                       // coupling operand: current / next item
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j)
+            rs[j] = (min_ok && xb0 < W) ? resp[(size_t)j * plane + (size_t)(sg.ya + 1) * Wp] : make_float4(0.f, 0.f, 0.f, 0.f);
+        BTC_ACC_BEGIN();
 #pragma unroll 1
         for (int y = sg.ya; y < sg.yb; ++y) {
             const int ly = y - sg.ya, sa = ly & (NA3 - 1);
@@ -600,23 +624,25 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                             (uint32_t)(max(min(NB * Cfg::XO, W - sg.x0), 1) * 16));
             const size_t rowoff = (size_t)(y + 1) * Wp;
             if (CPT == CH) {
-                // ---- all of this thread's couts fit in registers: one pass per block
-                float4 r[NB][CH / 4];                    // coupling operand, requested before the accumulator wait
-#pragma unroll
-                for (int blk = 0; blk < NB; ++blk)
-#pragma unroll
-                    for (int j = 0; j < CH / 4; ++j)
-                        r[blk][j] = (min_ok && xb0 + blk * Cfg::XO < W) ? resp[(size_t)j * plane + rowoff + blk * Cfg::XO]
-                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                mbar_wait_a(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
+                // ---- all of this thread's couts fit in registers: one pass per block.  The coupling operand of the
+                //      NEXT (row, block) item is requested before the current one is processed (rs/rn live across rows)
+                BTC_WAIT(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
                 tc_fence_after();
                 if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
 #pragma unroll
                 for (int blk = 0; blk < NB; ++blk, par ^= 1) {
                     const int x = xb0 + blk * Cfg::XO;
                     const bool xin = min_ok && (x < W);
+                    {   // next item: block blk+1 of this row, or block 0 of the next row
+                        const int nblk = (blk + 1 < NB) ? blk + 1 : 0;
+                        const int ny = (blk + 1 < NB) ? y : y + 1;
+                        const bool nin = min_ok && (xb0 + nblk * Cfg::XO < W) && (ny < sg.yb);
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j)
+                            rn[j] = nin ? resp[(size_t)j * plane + (size_t)(ny + 1) * Wp + nblk * Cfg::XO] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     const uint32_t trow = trow0 + blk * Cfg::ACOLS_BLK + sa * N3;
-                    float* ex = ex_base + par * (4 * 2 * C);
+                    const uint32_t ex = ex_base + (uint32_t)(par * (4 * 2 * C * 4));
                     uint32_t u0[CH], u1[CH], u2[CH];
                     tmem_ld8_nowait(trow + 0 * C, u0);
                     tmem_ld8_nowait(trow + 1 * C, u1);
@@ -634,8 +660,8 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     if (lane == 31 || lane == 0) {
 #pragma unroll
                         for (int i = 0; i < CH; i += 4)
-                            *reinterpret_cast<float4*>(ex + pub_off + i) = lane == 0 ? make_float4(v2[i], v2[i + 1], v2[i + 2], v2[i + 3])
-                                                                                     : make_float4(v0[i], v0[i + 1], v0[i + 2], v0[i + 3]);
+                            btc_sts128(ex + pub_off + 4 * i, lane == 0 ? make_uint4(u2[i], u2[i + 1], u2[i + 2], u2[i + 3])
+                                                                       : make_uint4(u0[i], u0[i + 1], u0[i + 2], u0[i + 3]));
                     }
                     if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 1);
                     named_barrier(3 + half, 128);
@@ -644,9 +670,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     float el[CH], er[CH], bb[CH];
 #pragma unroll
                     for (int i = 0; i < CH; i += 4) {       // warp-uniform addresses (broadcast), all issued before any use
-                        const float4 a4 = *reinterpret_cast<const float4*>(ex + l_off + i);
-                        const float4 c4 = *reinterpret_cast<const float4*>(ex + r_off + i);
-                        const float4 d4 = *reinterpret_cast<const float4*>(b3p + i);
+                        const float4 a4 = btc_lds128(ex + l_off + 4 * i), c4 = btc_lds128(ex + r_off + 4 * i), d4 = btc_lds128(b3p + 4 * i);
                         el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
                         er[i] = c4.x; er[i + 1] = c4.y; er[i + 2] = c4.z; er[i + 3] = c4.w;
                         bb[i] = d4.x; bb[i + 1] = d4.y; bb[i + 2] = d4.z; bb[i + 3] = d4.w;
@@ -663,26 +687,27 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     if (xin) {
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) {
-                            const float4 rr = r[blk][j];
+                            const float4 rr = rs[j];
                             float4 o;
                             o.x = rr.x + v1[4 * j]; o.y = rr.y + v1[4 * j + 1]; o.z = rr.z + v1[4 * j + 2]; o.w = rr.w + v1[4 * j + 3];
                             p4_store(outp + (size_t)j * plane, H, W, y, x, o);
                         }
                     }
                     if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 4);
+#pragma unroll
+                    for (int j = 0; j < CH / 4; ++j) rs[j] = rn[j];
                 }
             } else {
                 static_assert(CPT == CH || NB == 1, "the chunked E3 path handles one block per step");
                 const int x = xb0;
                 const bool xin = min_ok && (x < W);
-                float4 r[CH / 4], rn[CH / 4];            // coupling operand of the current / next cout chunk, requested early
 #pragma unroll
-                for (int j = 0; j < CH / 4; ++j) r[j] = xin ? resp[(size_t)j * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
-                mbar_wait_a(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
+                for (int j = 0; j < CH / 4; ++j) rs[j] = xin ? resp[(size_t)j * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
+                BTC_WAIT(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
                 tc_fence_after();
                 if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
                 const uint32_t trow = trow0 + sa * N3;
-                float* ex = ex_base + par * (4 * 2 * C);
+                const uint32_t ex = ex_base + (uint32_t)(par * (4 * 2 * C * 4));
                 par ^= 1;
                 // ---- phase 1: publish the partial sums the neighbouring warp needs (lane 31's kx=0, lane 0's kx=2)
 #pragma unroll
@@ -698,9 +723,8 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     if (lane == 31 || lane == 0) {
 #pragma unroll
                         for (int i = 0; i < CH; i += 4)
-                            *reinterpret_cast<float4*>(ex + pub_off + c0 + i) =
-                                lane == 0 ? make_float4(v2[i], v2[i + 1], v2[i + 2], v2[i + 3])
-                                          : make_float4(v0[i], v0[i + 1], v0[i + 2], v0[i + 3]);
+                            btc_sts128(ex + pub_off + 4 * (c0 + i), lane == 0 ? make_uint4(u2[i], u2[i + 1], u2[i + 2], u2[i + 3])
+                                                                              : make_uint4(u0[i], u0[i + 1], u0[i + 2], u0[i + 3]));
                     }
                 }
                 named_barrier(3 + half, 128);
@@ -708,7 +732,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                 // ---- phase 2
 #pragma unroll
                 for (int c0 = 0; c0 < CPT; c0 += CH) {
-                    if (c0 + CH < CPT) {
+                    if (c0 + CH < CPT) {        // next cout chunk of this row
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j)
                             rn[j] = xin ? resp[(size_t)((c0 + CH) / 4 + j) * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -716,9 +740,8 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     float el[CH], er[CH], bb[CH];
 #pragma unroll
                     for (int i = 0; i < CH; i += 4) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(ex + l_off + c0 + i);
-                        const float4 c4 = *reinterpret_cast<const float4*>(ex + r_off + c0 + i);
-                        const float4 d4 = *reinterpret_cast<const float4*>(b3p + c0 + i);
+                        const float4 a4 = btc_lds128(ex + l_off + 4 * (c0 + i)), c4 = btc_lds128(ex + r_off + 4 * (c0 + i)),
+                                     d4 = btc_lds128(b3p + 4 * (c0 + i));
                         el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
                         er[i] = c4.x; er[i + 1] = c4.y; er[i + 2] = c4.z; er[i + 3] = c4.w;
                         bb[i] = d4.x; bb[i + 1] = d4.y; bb[i + 2] = d4.z; bb[i + 3] = d4.w;
@@ -747,18 +770,21 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     if (xin) {
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) {
-                            const float4 rr = r[j];
+                            const float4 rr = rs[j];
                             float4 o;
                             o.x = rr.x + v1[4 * j]; o.y = rr.y + v1[4 * j + 1]; o.z = rr.z + v1[4 * j + 2]; o.w = rr.w + v1[4 * j + 3];
                             p4_store(outp + (size_t)(c0 / 4 + j) * plane, H, W, y, x, o);
                         }
                     }
+                    if (c0 + CH < CPT) {
 #pragma unroll
-                    for (int j = 0; j < CH / 4; ++j) r[j] = rn[j];
+                        for (int j = 0; j < CH / 4; ++j) rs[j] = rn[j];
+                    }
                 }
             }
             if (tid == 0) BTC_TRACE(4, 4 * ly + 3);
         }
+        if (tid == 0) BTC_ACC_END((a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr, 4, sg.yb - sg.ya);
     }
 
     tc_fence_before();
