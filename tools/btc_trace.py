@@ -28,6 +28,7 @@ show(0, "issuer", 6, ["begin", "conv3 go", "conv3 done", "conv2 go", "conv1 go",
 show(1, "converter", 3, ["begin", "x_empty ok", "arrived"])
 show(4, "E3", 4, ["begin", "acc ok", "barrier", "end"])
 show(5, "E3 block 0 detail", 8, ["tmem_ld done", "published", "barrier", "math done", "stored"])
+show(6, "E3 chunk detail (C=64)", 8, ["chunk0 start", "tmem done", "math done", "stored", "chunk1 done"])
 print("== per-role accounting: total cycles in the row loop, cycles inside barrier waits, steps")
 for role, name in [(0, "issuer"), (3, "converter"), (1, "E1"), (2, "E2"), (4, "E3")]:
     tot, wt, n = a[7][role * 8: role * 8 + 3]
