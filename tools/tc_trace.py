@@ -10,7 +10,7 @@ from vstnet_b200 import RevResNet, _lib
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-net = RevResNet(hidden_dim=16, sp_steps=2, precision="tf32x2").to(dev).eval()
+net = RevResNet(hidden_dim=16, sp_steps=2, precision=(sys.argv[2] if len(sys.argv) > 2 else "f16x2")).to(dev).eval()
 x = torch.rand(1, 3, 1080, 1920, device=dev)
 net(x); torch.cuda.synchronize()
 net(x); torch.cuda.synchronize()
@@ -23,4 +23,4 @@ t0 = a[a > 0].min()
 print("shape", shape, "rc", rc)
 for r in range(8):
     v = a[r][a[r] > 0] - t0
-    print("%-15s n=%4d : %s" % (names[r], len(v), " ".join("%7d" % q for q in v[:(40 if r == 7 else 20)])))
+    print("%-15s n=%4d : %s" % (names[r], len(v), " ".join("%7d" % q for q in v[:(40 if r == 7 else 36)])))

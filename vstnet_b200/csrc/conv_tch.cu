@@ -26,7 +26,7 @@ struct TchCfg {
     static constexpr int TA = TERMS >= 2 ? 2 : 1;   // activation terms (hi [, lo])
     static constexpr int TW = TERMS >= 3 ? 2 : 1;   // weight terms (hi [, lo])
     static constexpr int PW = 128;                  // staged pixels per row = UMMA M
-    static constexpr int XS = 126;                  // outputs per tile row
+    static constexpr int XS = 120;                  // outputs per tile row: four 32-row windows of 30 outputs + 2 halo pixels
     static constexpr int ROWS = R + 2;
     static constexpr int ROW_BYTES = PW * 16;       // one row of one 4-channel fp32 group == one row of one 8-channel fp16 k-half
     static constexpr int RAW_BYTES = 4 * ROWS * ROW_BYTES;          // 16 channels fp32
@@ -274,7 +274,10 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                 uint4* lo = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES + Cfg::A_TERM_BYTES);
 #pragma unroll 4
                 for (int i = ctid; i < 2 * ROWS * PW; i += 128) {
-                    const int kh = i / (ROWS * PW), rp = i - kh * (ROWS * PW);      // k-half, (row, pixel)
+                    const int kh = i / (ROWS * PW), rm = i - kh * (ROWS * PW);      // k-half, (row, operand row m)
+                    // operand row m = 32q + l of an image row holds staged pixel 30q + l: the kx fold of the epilogue
+                    // (m-1, m, m+1) then never leaves a warp's 32 TMEM lanes — no cross-warp exchange
+                    const int mm = rm & (PW - 1), rp = rm - mm + 30 * (mm >> 5) + (mm & 31);
                     const float4 u = raw[(2 * kh) * (ROWS * PW) + rp];
                     const float4 v = raw[(2 * kh + 1) * (ROWS * PW) + rp];
                     const float x[8] = {u.x * VST_HALF_SCALE, u.y * VST_HALF_SCALE, u.z * VST_HALF_SCALE, u.w * VST_HALF_SCALE,
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
         constexpr int HC = NC / 2;                         // couts per thread
         constexpr int CH = HC >= 16 ? 16 : HC;             // couts per TMEM load
         const int q = warp & 3, half = warp >> 2;
-        const int m = q * 32 + lane;
+        const int pm = q * 30 + lane;                      // staged pixel held by this thread's TMEM lane (window layout)
         const float flo = (a.epi == EPI_RELU) ? 0.f : -INFINITY;
         const int H = a.Hout, W = a.Wout, Wp = W + 2;
         const size_t plane = p4_plane_px(H, W);
@@ -310,34 +313,14 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
             const int ct = t % tl.n_ct, rest = t / tl.n_ct;
             const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * R;
             const uint32_t b = tcount % NACC;
-            const int x = xs - 1 + m;
-            const bool xin = (m >= 1) && (m <= XS) && (x < W);
+            const int x = xs - 1 + pm;
+            const bool xin = (lane >= 1) && (lane <= 30) && (x < W);
             const int rows = min(R, H - y0);
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * Cfg::ACC_COLS + half * HC;
-            float* ex = exch + (size_t)(tcount & 1) * (R * 4 * 2 * NC);
             mbar_wait(&acc_full[b], (tcount / NACC) & 1);
             tc_fence_after();
             if (tid == 0) TCH_TRACE(6, tcount);
-            // ---- phase 1: publish the partial sums a neighbouring warp needs (lane 31's kx=0, lane 0's kx=2)
-#pragma unroll 1
-            for (int r = 0; r < rows; ++r) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < HC; c0 += CH) {
-                    float v0[CH], v2[CH];
-                    tmem_ld2<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0, trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
-                    if (lane == 31) {
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) ex[((r * 4 + q) * 2 + 0) * NC + half * HC + c0 + i] = v0[i];
-                    }
-                    if (lane == 0) {
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) ex[((r * 4 + q) * 2 + 1) * NC + half * HC + c0 + i] = v2[i];
-                    }
-                }
-            }
-            named_barrier(1, 256);
-            if (tid == 0) TCH_TRACE(7, 2 * tcount);
-            // ---- phase 2: out[m] = D[m-1][kx=0] + D[m][kx=1] + D[m+1][kx=2]
+            // out[m] = D[m-1][kx=0] + D[m][kx=1] + D[m+1][kx=2], all within the warp
             const bool lf = xin && (x == 1), rt = xin && (x == W - 2);
 #pragma unroll 1
             for (int r = 0; r < rows; ++r) {
@@ -350,23 +333,10 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                                  trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
                     if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 0);
                     const int cb = half * HC + c0;                  // first cout of this chunk (within the tile)
-                    const float* exl = ex + ((r * 4 + (q > 0 ? q - 1 : 0)) * 2 + 0) * NC + cb;   // left neighbour warp, lane 31
-                    const float* exr = ex + ((r * 4 + (q < 3 ? q + 1 : 3)) * 2 + 1) * NC + cb;   // right neighbour warp, lane 0
-                    // neighbour-warp values: warp-uniform addresses (broadcast loads), selected without branching
-                    float el[CH], er[CH];
-#pragma unroll
-                    for (int i = 0; i < CH; i += 4) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(exl + i);
-                        const float4 b4 = *reinterpret_cast<const float4*>(exr + i);
-                        el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
-                        er[i] = b4.x; er[i + 1] = b4.y; er[i + 2] = b4.z; er[i + 3] = b4.w;
-                    }
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
-                        const float ls = __shfl_up_sync(0xffffffffu, v0[i], 1);
-                        const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
-                        const float l = (lane == 0) ? el[i] : ls;
-                        const float rr = (lane == 31) ? er[i] : rs;
+                        const float l = __shfl_up_sync(0xffffffffu, v0[i], 1);
+                        const float rr = __shfl_down_sync(0xffffffffu, v2[i], 1);
                         v1[i] = ((l + v1[i]) + rr) * (1.0f / VST_HALF_SCALE);
                     }
                     if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 1);
