@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
     constexpr int M = Cfg::M, G = Cfg::G, KS = Cfg::KS, N1 = Cfg::N1, N3 = Cfg::N3, TT = Cfg::TT, NX = Cfg::NX, NT = Cfg::NT;
     constexpr int NA1 = Cfg::NA1, NA2 = Cfg::NA2, NA3 = Cfg::NA3;
 
+    pdl_launch_dependents();             // the next kernel of the stream may start its prologue on SMs that drain
     const int H = a.H, W = a.W, Hp = H + 2, Wp = W + 2;
     BtcSeg sg;
     {
@@ -384,6 +385,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                          // everything above is independent of the previous kernel's output
 
     if (warp == 20) {
         // ================= weights (one TMA copy) + UMMA issuer =================
@@ -814,7 +816,7 @@ static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
     const double px = (double)a.H * a.W;
     ProfScope prof(st, C == 16 ? "rev_block_tc 16>4>4>16" : "rev_block_tc 64>16>16>64",
                    2.0 * 9 * (2.0 * C * Cfg::M + Cfg::M * Cfg::M) * px, 3.0 * 4.0 * C * px);
-    kern<<<a.n_strips * nseg, BTC_THREADS, Cfg::SMEM, st>>>(a);
+    VST_CUDA_OK(launch_pdl(kern, a.n_strips * nseg, BTC_THREADS, Cfg::SMEM, st, a));
     return check_launch("rev_block_tc");
 }
 

@@ -48,6 +48,26 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 int num_sms();
 
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains, so that its
+// prologue (barrier init, TMEM allocation, weight / bias staging — nothing that depends on the predecessor's output)
+// overlaps the predecessor's tail.  Such a kernel MUST execute pdl_wait() before its first access to dependent memory.
+// VST_PDL=0 (developer knob) launches plainly.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ---- optional per-launch device timing (cudaEvent pairs on the launch stream), aggregated by
 // kernel class; enabled by bench.py to obtain the live per-kernel durations of the roofline.
 bool prof_on();

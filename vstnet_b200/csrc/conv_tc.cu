@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
     uint64_t* acc_empty = bars + 3 * NS + 2;    // [2]   256 epilogue threads
     uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NS + 4);
     float* bias_s = (float*)((uint8_t*)bars + 1024);
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < a.Cout && i < 256; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                          // prologue above touches only constants (bias) and on-chip state
 
     // Roles are dispatched per warpgroup, each branch starting with its register-file rebalancing
     // (setmaxnreg): the epilogue keeps a whole tile of coupling operands in registers — that is the
@@ -427,7 +429,7 @@ static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
     const bool coupled = a.epi >= EPI_ADD;
     ProfScope prof(st, cls, 2.0 * 9 * a.Cin * a.Cout * px,
                    4.0 * ((double)a.Cin * a.Hin * a.Win + (coupled ? 2.0 : 1.0) * a.Cout * px));
-    kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(a, tl);
+    VST_CUDA_OK(launch_pdl(kern, grid, TC_THREADS, Cfg::SMEM, st, a, tl));
     return check_launch("conv3x3_tc");
 }
 

@@ -142,6 +142,7 @@ template <int NC, int R, int TERMS>
 __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a, TchTiles tl) {
     using Cfg = TchCfg<NC, R, TERMS>;
     constexpr int NR = Cfg::NR, NO = Cfg::NO, PW = Cfg::PW, ROWS = Cfg::ROWS, NP = Cfg::NP, NACC = Cfg::NACC, XS = Cfg::XS;
+    pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* raw_base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     uint8_t* op_base = raw_base + (size_t)NR * Cfg::RAW_BYTES;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                          // prologue above touches only constants (bias) and on-chip state
 
     if (warp == 12) {
         // ================= activation producer (TMA): raw fp32 P4 rows of 16 channels -> RAW ring =================
@@ -444,7 +446,7 @@ static int launch_tch_cfg(const ConvArgs& a, cudaStream_t st) {
     snprintf(cls, sizeof(cls), "conv3x3_tch%d %d>%d", TERMS, a.Cin, a.Cout);
     const double px = (double)a.Hout * a.Wout;
     ProfScope prof(st, cls, 2.0 * 9 * a.Cin * a.Cout * px, 4.0 * ((double)a.Cin * a.Hin * a.Win + a.Cout * px));
-    kern<<<grid, TCH_THREADS, Cfg::SMEM, st>>>(a, tl);
+    VST_CUDA_OK(launch_pdl(kern, grid, TCH_THREADS, Cfg::SMEM, st, a, tl));
     return check_launch("conv3x3_tch");
 }
 

@@ -3,6 +3,7 @@
 #include <vector>
 #include <mutex>
 #include <utility>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vst {
@@ -15,6 +16,12 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VST_PDL"); v = e ? atoi(e) : 1; }
+    return v != 0;
 }
 
 int num_sms() {
