@@ -238,6 +238,32 @@ def test_video_stylizer_matches_image_path(dev):
     assert out.shape == (72, 88, 3) and int((out.int() - ref8.int()).abs().max()) <= 1
 
 
+def test_video_multi_stream_paths_match_single_frame_path(dev):
+    """Frames dealt to several compute streams (stylize_frames) and the pipelined host path (stylize_stream,
+    ring of n_streams + 1 staging slots) return, in order, exactly what the one-frame calls return."""
+    from vstnet_b200.video import VideoStylizer
+    net = build_net("photo", 0, 7).to(dev)
+    g = torch.Generator().manual_seed(33)
+    style = torch.rand(1, 3, 64, 96, generator=g).to(dev)
+    frames = [torch.rand(1, 3, 72, 88, generator=g).to(dev) for _ in range(9)]
+    ref = VideoStylizer(net, n_streams=1)
+    ref.set_style(style)
+    want = [ref.stylize(f).clone() for f in frames]
+    for n in (1, 2, 3):
+        vs = VideoStylizer(net, n_streams=n)
+        vs.set_style(style)
+        got = [y.clone() for y in vs.stylize_frames(frames)]
+        torch.cuda.synchronize()
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        u8 = [(f[0].permute(1, 2, 0) * 255).round().clamp(0, 255).byte().cpu().pin_memory() for f in frames]
+        outs = [o.clone() for o in vs.stylize_stream(u8)]
+        assert len(outs) == len(u8)
+        for o, h in zip(outs, u8):
+            assert torch.equal(o, ref.stylize_host(h))
+
+
 def test_image_transfer_entry_point_synthetic(dev, tmp_path):
     import image_transfer
     y = image_transfer.main(["--synthetic", "64x96", "--out_dir", str(tmp_path)])
