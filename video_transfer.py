@@ -96,11 +96,16 @@ def main(argv=None):
     video_h, video_w = frames[0].shape[:2]
     mine = shard_frames(len(frames), rank, world)
     out = {}
-    for i in mine:
-        frame = Image.fromarray(frames[i])
-        frame = img_resize(frame, args.max_size, down_scale=RevNetwork.down_scale)      # ref :161
-        u8 = torch.from_numpy(np.array(frame))
-        out[i] = vs.stylize_host(u8, bgr=False).clone().numpy()                        # RGB uint8 HWC
+
+    def host_frames():
+        for i in mine:
+            frame = Image.fromarray(frames[i])
+            frame = img_resize(frame, args.max_size, down_scale=RevNetwork.down_scale)  # ref :161
+            yield torch.from_numpy(np.array(frame))
+
+    # pipelined host path: upload, n_streams frames in flight on the GPU, download (vstnet_b200/video.py)
+    for i, o in zip(mine, vs.stylize_stream(host_frames(), bgr=False)):
+        out[i] = o.clone().numpy()                                                     # RGB uint8 HWC
     # gather frames on rank 0 in frame order (host side; no device collective on the data path)
     if world > 1:
         gathered = [None] * world
