@@ -268,7 +268,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`)
-    for _ in vs.stylize_frames(frames[i % pool] for i in range(max(Wm, 2 * vs.n_streams))):
+    Wm = max(Wm, 4 * vs.n_streams)                    # every compute stream's workspace / allocator pool is warm
+    for _ in vs.stylize_frames(frames[i % pool] for i in range(Wm)):
         pass
     barrier()
     sampler = ClockSampler(local)
