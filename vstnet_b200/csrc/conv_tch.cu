@@ -136,7 +136,8 @@ struct TchTiles {
 };
 #define TCH_TRACE(role, idx) do { if (tl.trace && blockIdx.x == 0 && (idx) < 4096) tl.trace[(role) * 4096 + (idx)] = clock64(); } while (0)
 
-constexpr int TCH_THREADS = 480;   // 8 epilogue + 4 converter warps, activation producer, UMMA issuer, weight producer
+constexpr int TCH_NCW = 8;         // converter warps: with 4 the fp32 -> fp16 hi/lo conversion paces the MMA phase (traces)
+constexpr int TCH_THREADS = (8 + TCH_NCW + 3) * 32;   // 8 epilogue + converter warps, activation producer, UMMA issuer, weight producer
 
 template <int NC, int R, int TERMS>
 __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a, TchTiles tl) {
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     uint8_t* op_base = raw_base + (size_t)NR * Cfg::RAW_BYTES;
     uint64_t* bars = (uint64_t*)(op_base + (size_t)NO * Cfg::OP_BYTES);
     uint64_t* raw_full = bars;                  // [NR]    activation producer arrive.expect_tx + TMA bytes
-    uint64_t* raw_empty = bars + 4;             // [NR]    128 converter threads
+    uint64_t* raw_empty = bars + 4;             // [NR]    converter threads
     uint64_t* op_ready = bars + 8;              // [NO]    128 converter threads + weight producer arrive.expect_tx + TMA bytes
     uint64_t* op_empty = bars + 12;             // [NO]    tcgen05.commit
     uint64_t* acc_full = bars + 16;             // [NACC]  tcgen05.commit
@@ -162,19 +163,20 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     const int n_chunks = a.Cin / 16;
 
     if (tid == 0) {
-        for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
-        for (int s = 0; s < NO; ++s) { mbar_init(&op_ready[s], 129); mbar_init(&op_empty[s], 1); }
+        for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 32 * TCH_NCW); }
+        for (int s = 0; s < NO; ++s) { mbar_init(&op_ready[s], 32 * TCH_NCW + 1); mbar_init(&op_empty[s], 1); }
         for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
         fence_barrier_init();
     }
-    if (warp == 13) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    constexpr int W_PROD = 8 + TCH_NCW, W_MMA = W_PROD + 1, W_WGT = W_PROD + 2;
+    if (warp == W_MMA) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                          // prologue above touches only constants (bias) and on-chip state
 
-    if (warp == 12) {
+    if (warp == W_PROD) {
         // ================= activation producer (TMA): raw fp32 P4 rows of 16 channels -> RAW ring =================
         if (lane == 0) {
             const int Hp = a.Hin + 2, Wp = a.Win + 2;
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                 }
             }
         }
-    } else if (warp == 14) {
+    } else if (warp == W_WGT) {
         // ================= weight producer (TMA): fp16 weights of the chunk -> operand slot =================
         if (lane == 0) {
             uint32_t it = 0;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                 }
             }
         }
-    } else if (warp == 13) {
+    } else if (warp == W_MMA) {
         // ================= UMMA issuer =================
         if (lane == 0) {
             // kind::f16: D = F32 (bit 4), A = B = F16 (format 0), N at bit 17, M at bit 24
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
             }
         }
         __syncwarp();
-    } else if (warp >= 8 && warp < 12) {
+    } else if (warp >= 8 && warp < 8 + TCH_NCW) {
         // ================= converters: raw fp32 -> fp16 hi / lo in the K-major operand layout =================
         // one item = 8 channels (two P4 groups) of one pixel: 32 bytes in, 16 (hi) + 16 (lo) bytes out
         const int ctid = tid - 256;
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                 uint4* hi = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES);
                 uint4* lo = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES + Cfg::A_TERM_BYTES);
 #pragma unroll 4
-                for (int i = ctid; i < 2 * ROWS * PW; i += 128) {
+                for (int i = ctid; i < 2 * ROWS * PW; i += 32 * TCH_NCW) {
                     const int kh = i / (ROWS * PW), rm = i - kh * (ROWS * PW);      // k-half, (row, operand row m)
                     // operand row m = 32q + l of an image row holds staged pixel 30q + l: the kx fold of the epilogue
                     // (m-1, m, m+1) then never leaves a warp's 32 TMEM lanes — no cross-warp exchange
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 13) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
