@@ -28,8 +28,10 @@ struct TchCfg {
     static constexpr int PW = 128;                  // staged pixels per row = UMMA M
     static constexpr int XS = 120;                  // outputs per tile row: four 32-row windows of 30 outputs + 2 halo pixels
     static constexpr int ROWS = R + 2;
-    static constexpr int ROW_BYTES = PW * 16;       // one row of one 4-channel fp32 group == one row of one 8-channel fp16 k-half
-    static constexpr int RAW_BYTES = 4 * ROWS * ROW_BYTES;          // 16 channels fp32
+    static constexpr int ROW_BYTES = PW * 16;       // one row of one 8-channel fp16 k-half (operand layout)
+    static constexpr int RAW_PW = 122;              // raw pixels staged per row: the four windows cover pixels 0..121
+    static constexpr int RAW_ROW_BYTES = RAW_PW * 16;               // one row of one 4-channel fp32 group
+    static constexpr int RAW_BYTES = 4 * ROWS * RAW_ROW_BYTES;      // 16 channels fp32
     static constexpr int A_TERM_BYTES = 2 * ROWS * ROW_BYTES;       // 16 channels fp16: [k-half][row][pixel][8 halfs]
     static constexpr int A_BYTES = TA * A_TERM_BYTES;
     static constexpr int B_TERM_BYTES = 3 * 2 * NP * 16;            // [ky][k-half][n'][8 halfs]
@@ -38,8 +40,7 @@ struct TchCfg {
     static constexpr int ACC_COLS = R * NP;
     static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
-    static constexpr int EXCH_FLOATS = 2 * R * 4 * 2 * NC;          // [tile parity][row][warp quarter][side][cout]
-    static constexpr int AUX_BYTES = 2048 + EXCH_FLOATS * 4;        // barriers (1 KB) + bias (1 KB) + exchange
+    static constexpr int AUX_BYTES = 2048;                          // barriers (1 KB) + bias (1 KB)
     static constexpr int NO = 2;                                    // operand ring depth
     static constexpr int NR_FIT = (226 * 1024 - AUX_BYTES - NO * OP_BYTES) / RAW_BYTES;
     static constexpr int NR = NR_FIT > 4 ? 4 : NR_FIT;              // raw ring depth
@@ -156,7 +157,6 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     uint64_t* acc_empty = bars + 18;            // [NACC]  256 epilogue threads
     uint32_t* tmem_slot = (uint32_t*)(bars + 20);
     float* bias_s = (float*)((uint8_t*)bars + 1024);
-    float* exch = bias_s + 256;                 // [2][R][4][2][NC]
     for (int i = threadIdx.x; i < a.Cout && i < 256; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                         for (int row = 0; row < ROWS; ++row) {
                             const int py = min(y0 + row, Hp - 1);     // padded row of image row y0-1+row
                             // tile pixel p <-> padded column xs + p (image x = xs - 1 + p)
-                            bulk_g2s(A + (g * ROWS + row) * Cfg::ROW_BYTES,
-                                     in4 + ((size_t)(4 * c + g) * Hp + py) * Wp + xs, Cfg::ROW_BYTES, &raw_full[s]);
+                            bulk_g2s(A + (g * ROWS + row) * Cfg::RAW_ROW_BYTES,
+                                     in4 + ((size_t)(4 * c + g) * Hp + py) * Wp + xs, Cfg::RAW_ROW_BYTES, &raw_full[s]);
                         }
                 }
             }
@@ -281,9 +281,9 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                     const int kh = i / (ROWS * PW), rm = i - kh * (ROWS * PW);      // k-half, (row, operand row m)
                     // operand row m = 32q + l of an image row holds staged pixel 30q + l: the kx fold of the epilogue
                     // (m-1, m, m+1) then never leaves a warp's 32 TMEM lanes — no cross-warp exchange
-                    const int mm = rm & (PW - 1), rp = rm - mm + 30 * (mm >> 5) + (mm & 31);
-                    const float4 u = raw[(2 * kh) * (ROWS * PW) + rp];
-                    const float4 v = raw[(2 * kh + 1) * (ROWS * PW) + rp];
+                    const int mm = rm & (PW - 1), rp = (rm >> 7) * Cfg::RAW_PW + 30 * (mm >> 5) + (mm & 31);   // PW = 128
+                    const float4 u = raw[(2 * kh) * (ROWS * Cfg::RAW_PW) + rp];
+                    const float4 v = raw[(2 * kh + 1) * (ROWS * Cfg::RAW_PW) + rp];
                     const float x[8] = {u.x * VST_HALF_SCALE, u.y * VST_HALF_SCALE, u.z * VST_HALF_SCALE, u.w * VST_HALF_SCALE,
                                         v.x * VST_HALF_SCALE, v.y * VST_HALF_SCALE, v.z * VST_HALF_SCALE, v.w * VST_HALF_SCALE};
                     float h[8], l[8];
