@@ -299,6 +299,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                     for (int j = 0; j < NG; ++j)
                         res[r][j] = (coupled && xin && r < rows) ? resp[(size_t)j * plane + (size_t)r * Wp]
                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (coupled && (lane & 7) == 0) {
+                    // the coupling operand of this CTA's NEXT tile: pulled HBM -> L2 now (one 128-byte line per 8
+                    // lanes), so that its register loads at the top of the next tile find it in L2 — the epilogue
+                    // runs behind the UMMAs, so nothing else hides that latency
+                    const int tn = t + (int)gridDim.x;
+                    if (tn < tl.n_tiles) {
+                        const int ctn = tn % tl.n_ct, restn = tn / tl.n_ct;
+                        const int xn = (restn % tl.n_xt) * 128 + q * 32 + lane, yn = (restn / tl.n_xt) * R;
+                        if (xn < W) {
+                            const float4* rn = reinterpret_cast<const float4*>(a.res) + (size_t)(ctn * (N / 4) + half * NG) * plane +
+                                               (size_t)(yn + 1) * Wp + (xn + 1);
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+#pragma unroll
+                                for (int j = 0; j < NG; ++j)
+                                    if (yn + r < H) asm volatile("prefetch.global.L2 [%0];" ::"l"(rn + (size_t)j * plane + (size_t)r * Wp));
+                        }
+                    }
+                }
                 mbar_wait(&acc_full[b], (tcount >> 1) & 1);
                 tc_fence_after();
                 if (tid == 0) TC_TRACE(6, tcount);
