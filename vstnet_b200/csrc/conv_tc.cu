@@ -116,7 +116,7 @@ __device__ __forceinline__ void umma_f16_tc(uint32_t d_tmem, uint64_t a_desc, ui
 
 // HALF = true: the input is an H8 split-half tensor (kernels.cuh): hi and lo rows arrive by TMA already in
 // the K-major fp16 operand layout, there is no converter stage, and the UMMAs are kind::f16 with K = 16.
-template <int N, int R, int TERMS, bool HALF>
+template <int N, int R, int TERMS, bool HALF, bool SQZ>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, TcTiles tl) {
     using Cfg = TcCfg<N, R, TERMS, HALF>;
     constexpr int NS = Cfg::NS, PW = Cfg::PW, ROWS = Cfg::ROWS;
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_chunks = a.Cin / Cfg::KCH;
-    const bool hot = a.epi <= EPI_SUB;                       // branch-free epilogue; squeeze modes use the generic one
+    constexpr bool hot = !SQZ;                               // branch-free epilogue; the squeeze modes (SQZ) use generic addressing
+                                                             // in their own instantiation, so their code cannot cost the hot one registers
     const bool coupled = a.epi == EPI_ADD || a.epi == EPI_SUB;
 
     if (tid == 0) {
@@ -375,23 +376,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                     if (tid == 0) TC_TRACE(7, tcount * R + r);
                 }
             } else {
-                // ---- squeeze / unsqueeze coupling (one launch per pass): generic direct epilogue
+                // ---- squeeze / unsqueeze coupling (one launch per pass): generic addressing (conv_epi_res / conv_epi_store),
+                //      but the coupling operand of row r+1 is requested while row r is combined and stored, and that of
+                //      row 0 before the accumulator wait
+                constexpr int NGH = N / 8;                                // cout groups per thread per row
+                float4 rr[2][NGH];
+#pragma unroll
+                for (int j = 0; j < NGH; ++j)
+                    rr[0][j] = (xin && rows > 0) ? conv_epi_res(a, g0 + j, y0, x) : make_float4(0.f, 0.f, 0.f, 0.f);
                 mbar_wait(&acc_full[b], (tcount >> 1) & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int r = 0; r < rows; ++r) {
-                    const int y = y0 + r;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < N / 2; c0 += CH) {
-                        float v[CH];
-                        tmem_ld<CH>(trow + (uint32_t)(r * N + c0), v);
-                        if (xin) {
 #pragma unroll
-                            for (int jj = 0; jj < CH / 4; ++jj) {
-                                const int g = g0 + c0 / 4 + jj;
-                                const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * g);
-                                conv_epilogue(a, g, y, x, make_float4(v[4 * jj] * unscale + bv.x, v[4 * jj + 1] * unscale + bv.y,
-                                                                      v[4 * jj + 2] * unscale + bv.z, v[4 * jj + 3] * unscale + bv.w));
+                for (int r = 0; r < R; ++r) {
+                    if (r < rows) {                                       // warp-uniform
+                        const int y = y0 + r;
+                        if (r + 1 < R) {
+#pragma unroll
+                            for (int j = 0; j < NGH; ++j)
+                                rr[(r + 1) & 1][j] = (xin && r + 1 < rows) ? conv_epi_res(a, g0 + j, y + 1, x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int c0 = 0; c0 < N / 2; c0 += CH) {
+                            float v[CH];
+                            tmem_ld<CH>(trow + (uint32_t)(r * N + c0), v);
+                            if (xin) {
+#pragma unroll
+                                for (int jj = 0; jj < CH / 4; ++jj) {
+                                    const int g = g0 + c0 / 4 + jj;
+                                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * g);
+                                    conv_epi_store(a, g, y, x,
+                                                   make_float4(v[4 * jj] * unscale + bv.x, v[4 * jj + 1] * unscale + bv.y,
+                                                               v[4 * jj + 2] * unscale + bv.z, v[4 * jj + 3] * unscale + bv.w),
+                                                   rr[r & 1][c0 / 4 + jj]);
+                                }
                             }
                         }
                     }
@@ -428,11 +445,17 @@ long long* tc_trace_buffer(int Cin, int Cout, cudaStream_t st) {
     return buf;
 }
 
+template <int N, int R, int TERMS, bool HALF, bool SQZ>
+static int launch_tc_cfg2(const ConvArgs& a, cudaStream_t st);
 template <int N, int R, int TERMS, bool HALF = false>
 static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
+    return a.epi <= EPI_SUB ? launch_tc_cfg2<N, R, TERMS, HALF, false>(a, st) : launch_tc_cfg2<N, R, TERMS, HALF, true>(a, st);
+}
+template <int N, int R, int TERMS, bool HALF, bool SQZ>
+static int launch_tc_cfg2(const ConvArgs& a, cudaStream_t st) {
     using Cfg = TcCfg<N, R, TERMS, HALF>;
     static bool attr_set = false;
-    auto kern = conv3x3_tc_kernel<N, R, TERMS, HALF>;
+    auto kern = conv3x3_tc_kernel<N, R, TERMS, HALF, SQZ>;
     if (!attr_set) {
         VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
