@@ -140,7 +140,7 @@ struct TchTiles {
 constexpr int TCH_NCW = 8;         // converter warps: with 4 the fp32 -> fp16 hi/lo conversion paces the MMA phase (traces)
 constexpr int TCH_THREADS = (8 + TCH_NCW + 3) * 32;   // 8 epilogue + converter warps, activation producer, UMMA issuer, weight producer
 
-template <int NC, int R, int TERMS>
+template <int NC, int R, int TERMS, bool SPLIT>   // SPLIT: H8 split-half output (compile time: each variant keeps its own registers)
 __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a, TchTiles tl) {
     using Cfg = TchCfg<NC, R, TERMS>;
     constexpr int NR = Cfg::NR, NO = Cfg::NO, PW = Cfg::PW, ROWS = Cfg::ROWS, NP = Cfg::NP, NACC = Cfg::NACC, XS = Cfg::XS;
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                         v1[i] = ((l + v1[i]) + rr) * (1.0f / VST_HALF_SCALE);
                     }
                     if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 1);
-                    if (xin && a.out_split) {
+                    if (SPLIT && xin) {
                         // H8 split-half output (feeds a kind::f16 conv): 8 channels = one 16-byte unit of hi and of lo
 #pragma unroll
                         for (int j = 0; j < CH / 8; ++j) {
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                                 }
                             }
                         }
-                    } else if (xin) {
+                    } else if (!SPLIT && xin) {
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j) {
                             const int g = (ct * NC + cb) / 4 + j;
@@ -430,11 +430,17 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     }
 }
 
+template <int NC, int R, int TERMS, bool SPLIT>
+static int launch_tch_cfg2(const ConvArgs& a, cudaStream_t st);
 template <int NC, int R, int TERMS>
 static int launch_tch_cfg(const ConvArgs& a, cudaStream_t st) {
+    return a.out_split ? launch_tch_cfg2<NC, R, TERMS, true>(a, st) : launch_tch_cfg2<NC, R, TERMS, false>(a, st);
+}
+template <int NC, int R, int TERMS, bool SPLIT>
+static int launch_tch_cfg2(const ConvArgs& a, cudaStream_t st) {
     using Cfg = TchCfg<NC, R, TERMS>;
     static bool attr_set = false;
-    auto kern = conv3x3_tch_kernel<NC, R, TERMS>;
+    auto kern = conv3x3_tch_kernel<NC, R, TERMS, SPLIT>;
     if (!attr_set) {
         VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set = true;
