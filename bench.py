@@ -192,7 +192,7 @@ def image_configs_ms(dev, precision, with_cpu):
         sm = torch.from_numpy(blocky(size, size, 4, 2, [3, 1, 0, 2, 7, 6, 4, 5])).to(dev) if masked else None
 
         def run():
-            zc, zs = net(c), net(s)
+            zc, zs = net.encode_pair(c, s)               # what image_transfer.py's stylize() does
             if masked:
                 zcs = cw.transfer(zc, zs, cm, sm)
             elif alpha is not None:
@@ -201,7 +201,7 @@ def image_configs_ms(dev, precision, with_cpu):
                 zcs = cw.transfer(zc, zs)
             return net(zcs, forward=False)
 
-        for _ in range(2):
+        for _ in range(4):                    # allocator pools of both streams and the weight pack are warm
             run()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

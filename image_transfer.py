@@ -50,8 +50,11 @@ def build_network(mode, precision="f16x2"):
 def stylize(RevNetwork, cwct, content, style, content_seg=None, style_seg=None, alpha_c=None):
     """ref: image_transfer.py:172-201."""
     with torch.no_grad():
-        z_c = RevNetwork(content, forward=True)
-        z_s = RevNetwork(style, forward=True)
+        if hasattr(RevNetwork, "encode_pair"):                  # the two encodes of ref :181-182 on two streams
+            z_c, z_s = RevNetwork.encode_pair(content, style)
+        else:
+            z_c = RevNetwork(content, forward=True)
+            z_s = RevNetwork(style, forward=True)
         if alpha_c is not None and content_seg is None and style_seg is None:
             assert 0.0 <= alpha_c <= 1.0
             z_cs = cwct.interpolation(z_c, styl_feat_list=[z_s], alpha_s_list=[1.0], alpha_c=alpha_c)

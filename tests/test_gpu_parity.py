@@ -238,6 +238,15 @@ def test_video_stylizer_matches_image_path(dev):
     assert out.shape == (72, 88, 3) and int((out.int() - ref8.int()).abs().max()) <= 1
 
 
+def test_encode_pair_equals_sequential_encodes(dev):
+    net = build_net("photo", 0, 7).to(dev)
+    g = torch.Generator().manual_seed(44)
+    a, b = torch.rand(1, 3, 72, 88, generator=g).to(dev), torch.rand(1, 3, 40, 136, generator=g).to(dev)
+    za, zb = net.encode_pair(a, b)
+    torch.cuda.synchronize()
+    assert torch.equal(za, net(a)) and torch.equal(zb, net(b))
+
+
 def test_video_multi_stream_paths_match_single_frame_path(dev):
     """Frames dealt to several compute streams (stylize_frames) and the pipelined host path (stylize_stream,
     ring of n_streams + 1 staging slots) return, in order, exactly what the one-frame calls return."""
