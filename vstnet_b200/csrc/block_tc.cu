@@ -64,7 +64,7 @@ struct BtcCfg {
 };
 
 constexpr int BTC_THREADS = 672;
-constexpr int BTC_PREFETCH_ROWS = 6;     // L2 prefetch distance of the x / res row streams
+constexpr int BTC_PREFETCH_ROWS = 3;     // L2 prefetch distance of the x / res row streams (A/B: 3 and 1 equal, -4 % vs 6 or none; 12 is worse)
 
 struct BlockTcArgs {
     const float* x;        // P4 [C/4][H+2][W+2][4]  half-state F is evaluated on
