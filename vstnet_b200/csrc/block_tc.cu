@@ -41,7 +41,7 @@ struct BtcCfg {
     static constexpr int XT = (C / 8) * CHUNK;           // one term of an x row: [C/8 chunks][pixel][16 B]
     static constexpr int X_BLK = 2 * XT;
     static constexpr int X_SLOT = NB * X_BLK;
-    static constexpr int NX = 3;
+    static constexpr int NX = (C == 16) ? 4 : 3;         // x ring depth (C = 64: 3 x 32 KB is what fits)
     static constexpr int T_TERM = 2 * CHUNK;
     static constexpr int T_BLK = TT * T_TERM;
     static constexpr int T_SLOT = NB * T_BLK;
@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
     uint8_t* t2ring = t1ring + (size_t)NT * Cfg::T_SLOT;
     uint8_t* wsm = t2ring + (size_t)NT * Cfg::T_SLOT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + Cfg::WPACK_BYTES);
-    uint64_t* x_full = bars;              // [NX]  128 converter threads
-    uint64_t* x_empty = bars + 3;         // [NX]  tcgen05.commit
+    uint64_t* x_full = bars + 40;         // [NX <= 4]  128 converter threads
+    uint64_t* x_empty = bars + 44;        // [NX <= 4]  tcgen05.commit
     uint64_t* a1_full = bars + 6;         // [4]   tcgen05.commit   (no a1/a2 "empty" barriers: implied, see the issuer)
     uint64_t* t1_full = bars + 12;        // [4]   128 E1 threads
     uint64_t* t1_empty = bars + 16;       // [4]   tcgen05.commit
