@@ -607,7 +607,7 @@ static int launch_apply(const float* feat, float* out, int C, long long n, const
         attr_set = true;
     }
     long long tiles = (n + Cfg::PX - 1) / Cfg::PX;
-    int grid = (int)std::min<long long>(tiles, (long long)num_sms() * (CP == 32 ? 4 : 2));
+    int grid = (int)std::min<long long>(tiles, (long long)num_sms() * (CP == 32 ? 6 : 2));
     ProfScope prof(st, CP == 32 ? "cwct_apply c32" : "cwct_apply c128", 2.0 * C * C * (double)n,
                    8.0 * C * (double)n + (labels ? (double)n : 0.0));
     kern<<<grid, 256, Cfg::SMEM, st>>>(feat, out, C, n, labels, L, T, mu, beta, valid, tiles);
