@@ -3,14 +3,14 @@
 // (models/RevResNet.py:79-88 the three ReflectionPad2d(1)+Conv2d(3x3), :96-104 forward coupling, :106-116 inverse).
 // The quarter-width intermediates never leave the SM; HBM sees exactly: read x (+ halo rows), read res, write out.
 //
-// Geometry.  A CTA owns a vertical strip of 128 staged pixels (122 output columns: three 3x3 convs eat 3 columns
-// per side) and a segment of output rows [ya, yb); it streams DOWN the strip one image row per step, so there is no
+// Geometry.  A CTA owns a vertical strip of NB x 128 staged pixels (NB = 2 for C = 16; 122 output columns per block:
+// three 3x3 convs eat 3 columns per side) and a segment of output rows [ya, yb); it streams DOWN the strip one image row per step, so there is no
 // halo recompute in y except 3 rows at each end of a segment.  Tile pixel m <-> image column x0 - 3 + m.
 //
 // GEMM view (kx folded into N as in conv_tch.cu; every UMMA is M = 128 pixels of one row, kind::f16, K = 16):
 //     D[m, (kx, co)] += A[m, (row, ci)] * W[ky][ci, (kx, co)],       conv(x)[m] = D[m-1, kx=0] + D[m, kx=1] + D[m+1, kx=2]
 //   conv1 is INPUT-stationary: when x row r has been converted it is multiplied into the three t1 rows r+1, r, r-1
-//     (ky = 0, 1, 2) which accumulate in a 3-slot TMEM ring — an x row is staged once and freed at once.
+//     (ky = 0, 1, 2) which accumulate in a 4-slot TMEM ring — an x row is staged once and freed at once.
 //   conv2 / conv3 are OUTPUT-stationary over 4-slot shared-memory rings of t1 / t2 rows; the ReflectionPad2d rows
 //     of the intermediates (row -1 = row 1, row H = row H-2) are a choice of ring slot, the padded columns are two
 //     extra 16-byte stores by the thread that owns column 1 / W-2.
@@ -19,7 +19,10 @@
 //
 // Warp roles (672 threads): 0-7 E3 (acc3 -> +bias, coupling with res -> global P4 stores), 8-11 E1 (acc1 -> ReLU ->
 // t1 ring), 12-15 E2 (acc2 -> ReLU -> t2 ring), 16-19 converters (global fp32 P4 rows -> fp16 hi/lo operand rows),
-// 20 weights TMA + UMMA issuer + TMEM owner.  All hand-offs are mbarriers; waits are bounded (tc_ptx.cuh).
+// 20 weights TMA + UMMA issuer + TMEM owner.  All hand-offs are mbarriers; waits are bounded (tc_ptx.cuh).  Per step the
+// issuer runs conv3(y = r-7), conv2(i = r-4), conv1(x row r) in that order, which makes the "accumulator drained"
+// hand-offs of acc1 / acc2 implicit in the t-row barriers it waits for anyway.  Launched with programmatic dependent
+// launch: everything up to pdl_wait() (rings zeroed, barriers, TMEM, weight copy) overlaps the previous kernel's tail.
 #include <stdlib.h>
 #include "kernels.cuh"
 #include <cuda_fp16.h>
