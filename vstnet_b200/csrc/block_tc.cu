@@ -17,7 +17,7 @@
 // Arithmetic is that of the f16x2 mode (conv_tch.cu): activations 64*x = hi + lo in fp16, weights fp16, fp32 accumulate.
 // For C = 16 the 4-channel intermediates pack hi|lo into one K = 16 operand (weights duplicated), halving their UMMAs.
 //
-// Warp roles (672 threads): 0-7 E3 (acc3 -> +bias, coupling with res -> global P4 stores), 8-11 E1 (acc1 -> ReLU ->
+// Warp roles (C = 64: 672 threads; C = 16 has 16 E3 warps, 928 threads): 0-7 E3 (acc3 -> +bias, coupling with res -> global P4 stores), 8-11 E1 (acc1 -> ReLU ->
 // t1 ring), 12-15 E2 (acc2 -> ReLU -> t2 ring), 16-19 converters (global fp32 P4 rows -> fp16 hi/lo operand rows),
 // 20 weights TMA + UMMA issuer + TMEM owner.  All hand-offs are mbarriers; waits are bounded (tc_ptx.cuh).  Per step the
 // issuer runs conv3(y = r-7), conv2(i = r-4), conv1(x row r) in that order, which makes the "accumulator drained"
@@ -60,13 +60,17 @@ struct BtcCfg {
     static constexpr int EXCH_FLOATS = 2 * 2 * (4 * 2 * M) + 2 * (4 * 2 * C);   // E1, E2 (double-buffered) + E3
     static constexpr int AUX_BYTES = 512 + EXCH_FLOATS * 4;
     static constexpr size_t SMEM = (size_t)NX * X_SLOT + 2 * (size_t)NT * T_SLOT + WPACK_BYTES + AUX_BYTES + 1024;
-    static constexpr int CPT = C / 2;                        // couts per E3 thread
-    static constexpr int CH = 8;                             // couts per TMEM load / register chunk
+    static constexpr int E3W = (C == 16) ? 16 : 8;           // E3 warps: 4 lane quarters x NPART cout parts (more parallel roles beat
+                                                             // fatter ones here: every role is latency-bound per warp)
+    static constexpr int NPART = E3W / 4;
+    static constexpr int CPT = C / NPART;                    // couts per E3 thread
+    static constexpr int CH = CPT < 8 ? CPT : 8;             // couts per TMEM load / register chunk
+    static constexpr int W_E1 = E3W, W_E2 = E3W + 4, W_CONV = E3W + 8, W_MMA = E3W + 12;   // first warp of each role
+    static constexpr int THREADS = (E3W + 13) * 32;
     static_assert(ACOLS <= 512, "accumulators exceed TMEM");
     static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
-constexpr int BTC_THREADS = 672;
 constexpr int BTC_PREFETCH_ROWS = 3;     // L2 prefetch distance of the x / res row streams (A/B: 3 and 1 equal, -4 % vs 6 or none; 12 is worse)
 
 struct BlockTcArgs {
@@ -317,7 +321,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
 // the kernel
 // ------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArgs a) {
+__global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(BlockTcArgs a) {
     using Cfg = BtcCfg<C>;
     constexpr int M = Cfg::M, G = Cfg::G, KS = Cfg::KS, N1 = Cfg::N1, N3 = Cfg::N3, TT = Cfg::TT, NX = Cfg::NX, NT = Cfg::NT;
     constexpr int NA1 = Cfg::NA1, NA2 = Cfg::NA2, NA3 = Cfg::NA3;
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
     {
         uint4* z = reinterpret_cast<uint4*>(xring);
         const int n16 = (NX * Cfg::X_SLOT + 2 * NT * Cfg::T_SLOT) / 16;
-        for (int i = tid; i < n16; i += BTC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < n16; i += Cfg::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
         for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 128); mbar_init(&x_empty[s], 1); }
@@ -377,12 +381,12 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&a2_full[s], 1);
-            mbar_init(&a3_full[s], 1); mbar_init(&a3_empty[s], 256);
+            mbar_init(&a3_full[s], 1); mbar_init(&a3_empty[s], 32 * Cfg::E3W);
         }
         mbar_init(w_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 20) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    if (warp == Cfg::W_MMA) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                          // everything above is independent of the previous kernel's output
 
-    if (warp == 20) {
+    if (warp == Cfg::W_MMA) {
         // ================= weights (one TMA copy) + UMMA issuer =================
         // the whole warp walks the (warp-uniform) schedule; one elected lane issues the tcgen05 instructions
         {
@@ -512,9 +516,9 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
             if (lane == 0) BTC_ACC_END((a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr, 0, sg.yb + 7 - sg.xa);
         }
         __syncwarp();
-    } else if (warp >= 16) {
+    } else if (warp >= Cfg::W_CONV) {
         // ================= converters: fp32 P4 rows (global / L2) -> fp16 hi | lo operand rows =================
-        const int m = tid - 16 * 32;                                  // staged pixel (of every block)
+        const int m = tid - Cfg::W_CONV * 32;                         // staged pixel (of every block)
         constexpr int NB = Cfg::NB;
         const int pc0 = max(sg.x0 - 2, 0);
         int pcb[NB];                                                  // padded column per block (clamped: garbage pixels only)
@@ -577,10 +581,10 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
             if (++s == NX) { s = 0; pe ^= 1u; }
         }
         if (m == 0) BTC_ACC_END((a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr, 3, sg.xb - sg.xa + 1);
-    } else if (warp >= 8) {
+    } else if (warp >= Cfg::W_E1) {
         // ================= E1 (warps 8-11) / E2 (warps 12-15) =================
         mbar_wait_a(smem_u32(w_bar), 0u);
-        const bool second = warp >= 12;
+        const bool second = warp >= Cfg::W_E2;
         BtcMidArgs g;
         g.tacc = tmem_base + (second ? Cfg::A2 : Cfg::A1);
         g.acc_full = smem_u32(second ? a2_full : a1_full);
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
     } else {
         // ================= E3: acc3 -> kx fold, bias, coupling with res -> global P4 (+ reflection border) =================
         constexpr int CPT = Cfg::CPT, CH = Cfg::CH, NB = Cfg::NB;
-        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;       // half = cout part of this warp (0 .. NPART-1)
         const int xb0 = sg.x0 - 3 + m;                                       // image column of this thread in block 0
         const bool min_ok = (m >= 3) && (m < 3 + Cfg::XO);
         const size_t plane = (size_t)Hp * Wp;
@@ -649,9 +653,9 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
                     const uint32_t trow = trow0 + blk * Cfg::ACOLS_BLK + sa * N3;
                     const uint32_t ex = ex_base + (uint32_t)(par * (4 * 2 * C * 4));
                     uint32_t u0[CH], u1[CH], u2[CH];
-                    tmem_ld8_nowait(trow + 0 * C, u0);
-                    tmem_ld8_nowait(trow + 1 * C, u1);
-                    tmem_ld8_nowait(trow + 2 * C, u2);
+                    tmem_ld_nowait<CH>(trow + 0 * C, u0);
+                    tmem_ld_nowait<CH>(trow + 1 * C, u1);
+                    tmem_ld_nowait<CH>(trow + 2 * C, u2);
                     tmem_ld_wait();
                     tmem_ld_fence_regs<CH>(u0); tmem_ld_fence_regs<CH>(u1); tmem_ld_fence_regs<CH>(u2);
                     float v0[CH], v1[CH], v2[CH];
@@ -794,7 +798,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) rev_block_tc_kernel(BlockTcArg
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 20) {
+    if (warp == Cfg::W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
@@ -819,7 +823,7 @@ static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
     const double px = (double)a.H * a.W;
     ProfScope prof(st, C == 16 ? "rev_block_tc 16>4>4>16" : "rev_block_tc 64>16>16>64",
                    2.0 * 9 * (2.0 * C * Cfg::M + Cfg::M * Cfg::M) * px, 3.0 * 4.0 * C * px);
-    VST_CUDA_OK(launch_pdl(kern, a.n_strips * nseg, BTC_THREADS, Cfg::SMEM, st, a));
+    VST_CUDA_OK(launch_pdl(kern, a.n_strips * nseg, Cfg::THREADS, Cfg::SMEM, st, a));
     return check_launch("rev_block_tc");
 }
 

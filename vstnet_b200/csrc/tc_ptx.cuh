@@ -160,6 +160,11 @@ __device__ __forceinline__ void tmem_ld_fence_regs(uint32_t* r) {
 #pragma unroll
     for (int i = 0; i < N; ++i) asm volatile("" : "+r"(r[i]));
 }
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -175,8 +180,10 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 
 template <int NC>
 __device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t* r) {
-    if (NC == 8) tmem_ld8_nowait(taddr, r);
-    else { static_assert(NC == 8 || NC == 16, "8 or 16 columns"); tmem_ld16_nowait(taddr, r); }
+    static_assert(NC == 4 || NC == 8 || NC == 16, "4, 8 or 16 columns");
+    if (NC == 4) tmem_ld4_nowait(taddr, r);
+    else if (NC == 8) tmem_ld8_nowait(taddr, r);
+    else tmem_ld16_nowait(taddr, r);
 }
 // 2 or 3 column blocks of NC columns each: loads issued back to back, ONE wait
 template <int NC>
