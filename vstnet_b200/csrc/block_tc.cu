@@ -60,7 +60,7 @@ struct BtcCfg {
     static constexpr int EXCH_FLOATS = 2 * 2 * (4 * 2 * M) + 2 * (4 * 2 * C);   // E1, E2 (double-buffered) + E3
     static constexpr int AUX_BYTES = 512 + EXCH_FLOATS * 4;
     static constexpr size_t SMEM = (size_t)NX * X_SLOT + 2 * (size_t)NT * T_SLOT + WPACK_BYTES + AUX_BYTES + 1024;
-    static constexpr int E3W = (C == 16) ? 16 : 8;           // E3 warps: 4 lane quarters x NPART cout parts (more parallel roles beat
+    static constexpr int E3W = 16;                           // E3 warps: 4 lane quarters x NPART cout parts (more parallel roles beat
                                                              // fatter ones here: every role is latency-bound per warp)
     static constexpr int NPART = E3W / 4;
     static constexpr int CPT = C / NPART;                    // couts per E3 thread
