@@ -233,11 +233,9 @@ template <int C>
 static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     using Cfg = BtcCfg<C>;
     constexpr int M = Cfg::M, N = Cfg::N1;
+    constexpr int MP = M > 8 ? 8 : M, NPASS = M / MP;     // channels per pass: M = 16 runs two passes of 8 (register budget: 64)
     const int lane = threadIdx.x & 31, q = (threadIdx.x >> 5) & 3;
     const int m = q * 32 + lane;
-    float bs[M];
-#pragma unroll
-    for (int c = 0; c < M; ++c) bs[c] = btc_lds(g.bias + 4 * c);
     const uint32_t ex_pub = g.exch + (uint32_t)((q * 2 + (lane == 0 ? 1 : 0)) * M * 4);      // where lane 31 / lane 0 publish
     const uint32_t ex_l = g.exch + (uint32_t)(((q > 0 ? q - 1 : 0) * 2 + 0) * M * 4);          // left warp's lane 31, kx = 0
     const uint32_t ex_r = g.exch + (uint32_t)(((q < 3 ? q + 1 : 3) * 2 + 1) * M * 4);          // right warp's lane 0, kx = 2
@@ -254,56 +252,64 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
             const int x = g.x0 + blk * Cfg::XO - 3 + m;
             const bool own = (x >= 0) && (x < g.W);
             const bool mir_l = (x == 1) && (m >= 2), mir_r = (x == g.W - 2) && (m + 2 < Cfg::PW);
-            uint32_t du[3 * M < 16 ? 16 : 3 * M];
-            if (M == 4) {
-                tmem_ld16_nowait(trow + (uint32_t)(blk * Cfg::ACOLS_BLK + sa * N), du);
-            } else {
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) tmem_ld16_nowait(trow + (uint32_t)(blk * Cfg::ACOLS_BLK + sa * N + kx * 16), du + kx * 16);
-            }
-            tmem_ld_wait();
-            tmem_ld_fence_regs<(3 * M < 16 ? 16 : 3 * M)>(du);
-            float d[3 * M < 16 ? 16 : 3 * M];
-#pragma unroll
-            for (int c = 0; c < (3 * M < 16 ? 16 : 3 * M); ++c) d[c] = __uint_as_float(du[c]);
-            if (lane == 31 || lane == 0) {
-#pragma unroll
-                for (int c = 0; c < M; ++c) btc_sts(ex_pub + par + 4 * c, lane == 0 ? d[2 * M + c] : d[c]);
-            }
-            named_barrier(g.bar_id, 128);
-            // neighbour-warp partial sums: warp-uniform addresses (broadcast loads), all issued before any use
-            float el[M], er[M];
-#pragma unroll
-            for (int c = 0; c < M; c += 4) {
-                const float4 a4 = btc_lds128(ex_l + par + 4 * c), b4 = btc_lds128(ex_r + par + 4 * c);
-                el[c] = a4.x; el[c + 1] = a4.y; el[c + 2] = a4.z; el[c + 3] = a4.w;
-                er[c] = b4.x; er[c + 1] = b4.y; er[c + 2] = b4.z; er[c + 3] = b4.w;
-            }
-            float o[M];
-#pragma unroll
-            for (int c = 0; c < M; ++c) {
-                const float ls = __shfl_up_sync(0xffffffffu, d[c], 1);
-                const float rs = __shfl_down_sync(0xffffffffu, d[2 * M + c], 1);
-                const float lv = (lane == 0) ? el[c] : ls;
-                const float rv = (lane == 31) ? er[c] : rs;
-                o[c] = fmaxf(((lv + d[M + c]) + rv) * (1.0f / VST_HALF_SCALE) + bs[c], 0.f) * VST_HALF_SCALE;
-            }
-            if (blk == 0) BTC_WAIT(g.t_empty + 8 * st, (uint32_t)(((l >> 2) & 1) ^ 1));
             const uint32_t slot = g.tring + (uint32_t)(st * Cfg::T_SLOT + blk * Cfg::T_BLK + m * 16);
-            if (M == 4) {
-                const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const uint4 v = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23),
-                                           btc_pack_half2(o[0] - f01.x, o[1] - f01.y), btc_pack_half2(o[2] - f23.x, o[3] - f23.y));
-                if (own) btc_sts128(slot, v);
-                if (mir_l) btc_sts128(slot - 32, v);
-                if (mir_r) btc_sts128(slot + 32, v);
-            } else {
+#pragma unroll 1
+            for (int ps = 0; ps < NPASS; ++ps) {
+                // D columns of this pass: [kx][MP channels]
+                uint32_t du[3 * MP < 16 ? 16 : 3 * MP];
+                if (M == 4) {
+                    tmem_ld16_nowait(trow + (uint32_t)(blk * Cfg::ACOLS_BLK + sa * N), du);      // 12 of the 16 padded columns
+                } else {
 #pragma unroll
-                for (int k = 0; k < M / 8; ++k) {
+                    for (int kx = 0; kx < 3; ++kx)
+                        tmem_ld8_nowait(trow + (uint32_t)(blk * Cfg::ACOLS_BLK + sa * N + kx * M + ps * MP), du + kx * MP);
+                }
+                float bs[MP];
+#pragma unroll
+                for (int c = 0; c < MP; c += 4) {
+                    const float4 b4 = btc_lds128(g.bias + 4 * (ps * MP + c));
+                    bs[c] = b4.x; bs[c + 1] = b4.y; bs[c + 2] = b4.z; bs[c + 3] = b4.w;
+                }
+                tmem_ld_wait();
+                tmem_ld_fence_regs<(3 * MP < 16 ? 16 : 3 * MP)>(du);
+                float d[3 * MP];
+#pragma unroll
+                for (int c = 0; c < 3 * MP; ++c) d[c] = __uint_as_float(du[c]);
+                if (lane == 31 || lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < MP; ++c) btc_sts(ex_pub + par + 4 * (ps * MP + c), lane == 0 ? d[2 * MP + c] : d[c]);
+                }
+                named_barrier(g.bar_id, 128);
+                // neighbour-warp partial sums: warp-uniform addresses (broadcast loads), all issued before any use
+                float el[MP], er[MP];
+#pragma unroll
+                for (int c = 0; c < MP; c += 4) {
+                    const float4 a4 = btc_lds128(ex_l + par + 4 * (ps * MP + c)), b4 = btc_lds128(ex_r + par + 4 * (ps * MP + c));
+                    el[c] = a4.x; el[c + 1] = a4.y; el[c + 2] = a4.z; el[c + 3] = a4.w;
+                    er[c] = b4.x; er[c + 1] = b4.y; er[c + 2] = b4.z; er[c + 3] = b4.w;
+                }
+                float o[MP];
+#pragma unroll
+                for (int c = 0; c < MP; ++c) {
+                    const float ls = __shfl_up_sync(0xffffffffu, d[c], 1);
+                    const float rs = __shfl_down_sync(0xffffffffu, d[2 * MP + c], 1);
+                    const float lv = (lane == 0) ? el[c] : ls;
+                    const float rv = (lane == 31) ? er[c] : rs;
+                    o[c] = fmaxf(((lv + d[MP + c]) + rv) * (1.0f / VST_HALF_SCALE) + bs[c], 0.f) * VST_HALF_SCALE;
+                }
+                if (blk == 0 && ps == 0) BTC_WAIT(g.t_empty + 8 * st, (uint32_t)(((l >> 2) & 1) ^ 1));
+                if (M == 4) {
+                    const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const uint4 v = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23),
+                                               btc_pack_half2(o[0] - f01.x, o[1] - f01.y), btc_pack_half2(o[2] - f23.x, o[3] - f23.y));
+                    if (own) btc_sts128(slot, v);
+                    if (mir_l) btc_sts128(slot - 32, v);
+                    if (mir_r) btc_sts128(slot + 32, v);
+                } else {
                     uint4 hv, lv;
-                    btc_split8(o + 8 * k, hv, lv);
-                    const uint32_t ph = slot + k * Cfg::CHUNK, pl = ph + Cfg::T_TERM;      // term 0 (hi) / term 1 (lo), chunk k
+                    btc_split8(o, hv, lv);
+                    const uint32_t ph = slot + ps * Cfg::CHUNK, pl = ph + Cfg::T_TERM;     // term 0 (hi) / term 1 (lo), K chunk ps
                     if (own) { btc_sts128(ph, hv); btc_sts128(pl, lv); }
                     if (mir_l) { btc_sts128(ph - 32, hv); btc_sts128(pl - 32, lv); }
                     if (mir_r) { btc_sts128(ph + 32, hv); btc_sts128(pl + 32, lv); }
