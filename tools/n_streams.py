@@ -8,7 +8,7 @@ net = RevResNet(hidden_dim=16, sp_steps=2).to(dev).eval()
 H, W = 1080, 1920
 frames = [torch.rand(1, 3, H, W, device=dev) for _ in range(4)]
 style = torch.rand(1, 3, H, W, device=dev)
-for ns in (1, 2, 3, 4, 6, 3):
+for ns in (1, 3, 4, 5, 6, 8, 4):
     vs = VideoStylizer(net, n_streams=ns); vs.set_style(style)
     for _ in vs.stylize_frames(frames[i % 4] for i in range(2 * ns + 2)): pass
     torch.cuda.synchronize(); t0 = time.perf_counter()
