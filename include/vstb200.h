@@ -147,6 +147,10 @@ int vst_cwct_apply(const float* feat, float* out, int C, long long n, const uint
  * ----------------------------------------------------------------------------------------- */
 /* uint8 HWC (RGB or BGR) -> fp32 CHW RGB in [0,1]  (ToTensor, video_transfer.py:188) */
 int vst_frame_u8_to_f32(const uint8_t* hwc, float* chw, int H, int W, int bgr, void* stream);
+/* label map [Hs][Ws] -> [Hd][Wd], nearest neighbour with PIL Image.NEAREST sampling: the reference's cWCT.resize
+ * (models/cWCT.py:191-197; its call at :72-73 is commented out in this fork).  SURVEY.md 8(f) rank 3. */
+int vst_mask_resize_nearest(const uint8_t* src, int Hs, int Ws, uint8_t* dst, int Hd, int Wd,
+                            int* scratch /* Hd + Wd ints, device */, void* stream);
 /* fp32 CHW -> uint8 HWC, mul(255).clamp(0,255).byte() truncation (video_transfer.py:211-214) */
 int vst_frame_f32_to_u8(const float* chw, uint8_t* hwc, int H, int W, int bgr, void* stream);
 

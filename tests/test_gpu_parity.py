@@ -238,6 +238,40 @@ def test_video_stylizer_matches_image_path(dev):
     assert out.shape == (72, 88, 3) and int((out.int() - ref8.int()).abs().max()) <= 1
 
 
+def test_mask_resize_matches_pil_nearest(dev):
+    """vst_mask_resize_nearest == the reference's cWCT.resize (PIL Image.NEAREST, cWCT.py:191-197)."""
+    from PIL import Image
+    from vstnet_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for (hs, ws), (hd, wd) in [((64, 96), (32, 48)), ((37, 53), (64, 80)), ((1024, 1024), (512, 512)), ((90, 70), (33, 129)),
+                                 ((499, 323), (211, 457)), ((7, 5), (300, 400))]:
+        a = rng.integers(0, 9, (hs, ws), dtype=np.uint8)
+        want = np.array(Image.fromarray(a).resize((wd, hd), Image.NEAREST))
+        src = torch.from_numpy(a).to(dev)
+        dst = torch.empty(hd, wd, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(hd + wd, dtype=torch.int32, device=dev)
+        _lib.check(lib.vst_mask_resize_nearest(src.data_ptr(), hs, ws, dst.data_ptr(), hd, wd, scratch.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream), "vst_mask_resize_nearest")
+        assert np.array_equal(dst.cpu().numpy(), want), ((hs, ws), (hd, wd))
+
+
+def test_masked_transfer_with_image_resolution_masks_artistic(dev):
+    """Masks given at IMAGE resolution are brought to latent resolution on the device (the reference's disabled
+    cWCT.resize): the artistic latent is half the image size, so this is what makes masked artistic transfer work."""
+    from PIL import Image
+    from vstnet_b200 import cWCT
+    g = torch.Generator().manual_seed(8)
+    zc, zs = torch.randn(1, 128, 24, 40, generator=g), torch.randn(1, 128, 28, 36, generator=g)
+    cm = blocky_mask(48, 80, 2, 2, [0, 1, 2, 3])            # image resolution = 2 x latent
+    sm = blocky_mask(56, 72, 2, 2, [2, 0, 3, 1])
+    cm_l = np.array(Image.fromarray(cm[0]).resize((40, 24), Image.NEAREST))[None]
+    sm_l = np.array(Image.fromarray(sm[0]).resize((36, 28), Image.NEAREST))[None]
+    want = O.cwct_transfer_seg(zc.clone(), zs, cm_l, sm_l)
+    got = cWCT().transfer(zc.to(dev), zs.to(dev), cm, sm)
+    assert maxdiff(got, want) <= 5e-4
+
+
 def test_hot_path_is_deterministic_run_to_run(dev):
     """The role pipelines of the tcgen05 kernels (mbarrier rings, TMEM slots, PDL overlap, several frames in flight)
     must not race: repeated runs on the same inputs are bit-identical."""

@@ -75,23 +75,35 @@ class cWCT(nn.Module):
                                             mu.data_ptr(), beta.data_ptr(), valid.data_ptr(), stream), "vst_cwct_apply")
 
     @staticmethod
-    def _mask_to_device(mask, n, device, what):
-        """One sample's label map -> flat uint8 device tensor of n labels (+ its max label)."""
+    def _mask_to_device(mask, n, device, what, hw=None):
+        """One sample's label map -> flat uint8 device tensor of n labels (+ its max label).  A 2-D map whose
+        size differs from the latent's ``hw = (H, W)`` is resized on the device, nearest neighbour with PIL's
+        sampling — the reference's ``cWCT.resize`` (cWCT.py:191-197), whose call this fork comments out
+        (:72-73), so that there masks must already be at latent resolution (never true in artistic mode)."""
         if isinstance(mask, torch.Tensor):
             if mask.dtype != torch.uint8:
                 raise ValueError("%s must be uint8" % what)
-            m = mask.reshape(-1).to(device).contiguous()
-            mx = int(m.max().item())
+            m2 = mask.to(device)
         else:
             a = np.ascontiguousarray(np.asarray(mask))
             if a.dtype != np.uint8:
                 raise ValueError("%s must be uint8 (got %s)" % (what, a.dtype))
-            mx = int(a.max())
-            m = torch.from_numpy(a.reshape(-1)).to(device, non_blocking=False)
+            m2 = torch.from_numpy(a).to(device, non_blocking=False)
+        if m2.numel() != n and hw is not None and m2.dim() == 2:
+            src = m2.contiguous()
+            dst = torch.empty(hw[0] * hw[1], dtype=torch.uint8, device=device)
+            scratch = torch.empty(hw[0] + hw[1], dtype=torch.int32, device=device)
+            lib = _lib.load()
+            _lib.check(lib.vst_mask_resize_nearest(src.data_ptr(), int(src.shape[0]), int(src.shape[1]), dst.data_ptr(),
+                                                   int(hw[0]), int(hw[1]), scratch.data_ptr(),
+                                                   torch.cuda.current_stream(device).cuda_stream),
+                       "vst_mask_resize_nearest")
+            m2 = dst
+        m = m2.reshape(-1).contiguous()
         if m.numel() != n:
-            raise ValueError("%s has %d labels but the feature map has %d positions; masks must be at latent "
-                             "resolution (ref: cWCT.py:72-73)" % (what, m.numel(), n))
-        return m, mx
+            raise ValueError("%s has %d labels but the feature map has %d positions; masks must be 2-D label maps or "
+                             "flat maps at latent resolution (ref: cWCT.py:72-73)" % (what, m.numel(), n))
+        return m, int(m.max().item())
 
     # ------------------------------------------------------------------ reference API
     def transfer(self, content_feat, style_feat, cmask=None, smask=None):
@@ -149,7 +161,7 @@ class cWCT(nn.Module):
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             if smask is not None:
-                masks = [self._mask_to_device(smask[i], ns, dev, "smask") for i in range(B)]
+                masks = [self._mask_to_device(smask[i], ns, dev, "smask", (sH, sW)) for i in range(B)]
                 L = min(max(mx for _, mx in masks) + 1, 255)
             for i in range(B):
                 stats.append(self._stats(style[i], N, ns, masks[i][0] if smask is not None else None, L, st))
@@ -173,7 +185,7 @@ class cWCT(nn.Module):
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             for i in range(B):
-                cm = self._mask_to_device(cmask[i], n, dev, "cmask")[0] if masked else None
+                cm = self._mask_to_device(cmask[i], n, dev, "cmask", (cH, cW))[0] if masked else None
                 cst = self._stats(content[i], N, n, cm, L, st)
                 T, mu, beta, valid = self._factor(cst, [style_pre["stats"][i]], [1.0], 0.0 if masked else alpha_c, N, L,
                                                   masked, dev, st)
@@ -200,8 +212,8 @@ class cWCT(nn.Module):
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             for i in range(B):
-                cm, cmax = self._mask_to_device(cmask[i], nc, dev, "cmask")
-                sm, _ = self._mask_to_device(smask[i], ns, dev, "smask")
+                cm, cmax = self._mask_to_device(cmask[i], nc, dev, "cmask", (cH, cW))
+                sm, _ = self._mask_to_device(smask[i], ns, dev, "smask", (sH, sW))
                 # the reference sizes its validity table max(content label)+1 (cWCT.py:173-175);
                 # label 255 overflows its uint8 arithmetic there and raises IndexError.
                 if cmax >= 255:

@@ -266,6 +266,43 @@ __global__ void f32_to_u8_kernel(const float* __restrict__ chw, uint8_t* __restr
 
 }  // namespace vst
 
+// label map resize, nearest neighbour with PIL's Image.NEAREST sampling: the reference's cWCT.resize
+// (models/cWCT.py:191-197), which this fork leaves commented out at :72-73 — masked transfer then only works when
+// the masks already have the latent resolution (never in artistic mode).  PIL walks each axis with an accumulated
+// double, xo = 0.5 * s; index = (int)xo; xo += s  (s = src / dst); the index tables are built the same way (one
+// thread per axis: the accumulation order is part of the result at exact-integer sample points).
+__global__ void mask_resize_tables_kernel(int Hs, int Ws, int Hd, int Wd, int* __restrict__ iy, int* __restrict__ ix) {
+    const int axis = threadIdx.x;                       // 0: rows, 1: columns
+    if (axis > 1) return;
+    const int ns = axis ? Ws : Hs, nd = axis ? Wd : Hd;
+    int* t = axis ? ix : iy;
+    const double sc = (double)ns / (double)nd;
+    double xo = sc * 0.5;
+    for (int k = 0; k < nd; ++k) {
+        t[k] = min((int)xo, ns - 1);
+        xo += sc;
+    }
+}
+__global__ void mask_resize_nearest_kernel(const uint8_t* __restrict__ src, int Ws, uint8_t* __restrict__ dst, int Hd, int Wd,
+                                           const int* __restrict__ iy, const int* __restrict__ ix) {
+    const int n = Hd * Wd;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int y = i / Wd, x = i - y * Wd;
+        dst[i] = src[(size_t)iy[y] * Ws + ix[x]];
+    }
+}
+extern "C" int vst_mask_resize_nearest(const uint8_t* src, int Hs, int Ws, uint8_t* dst, int Hd, int Wd, int* scratch,
+                                       void* stream) {
+    using namespace vst;
+    VST_REQUIRE(src && dst && scratch && Hs > 0 && Ws > 0 && Hd > 0 && Wd > 0, "vst_mask_resize_nearest: bad arguments");
+    const int n = Hd * Wd;
+    mask_resize_tables_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(Hs, Ws, Hd, Wd, scratch, scratch + Hd);
+    if (check_launch("mask_resize_tables")) return 1;
+    mask_resize_nearest_kernel<<<std::min(cdiv(n, 256), 4096), 256, 0, (cudaStream_t)stream>>>(src, Ws, dst, Hd, Wd, scratch,
+                                                                                              scratch + Hd);
+    return check_launch("mask_resize_nearest");
+}
+
 extern "C" int vst_frame_u8_to_f32(const uint8_t* hwc, float* chw, int H, int W, int bgr, void* stream) {
     using namespace vst;
     VST_REQUIRE(hwc && chw && H > 0 && W > 0, "vst_frame_u8_to_f32: bad arguments");
