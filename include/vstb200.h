@@ -92,7 +92,12 @@ size_t vst_revnet_param_floats(const vst_revnet* net);
 size_t vst_revnet_packed_bytes(const vst_revnet* net);
 int vst_revnet_pack_weights(const vst_revnet* net, const float* raw_params, void* packed, void* stream);
 
-/* scratch needed by forward / inverse for a B x 3 x H x W image (H, W multiples of down_scale) */
+/* scratch needed by forward / inverse for a B x 3 x H x W image (H, W multiples of down_scale).
+ * The first 4 bytes of the workspace are an int32 STATUS WORD that every forward / inverse call clears in its first
+ * kernel and that is valid once the call's stream work has completed (the library never synchronises):
+ *   bit 0 (VST_STATUS_F16_RANGE): precision VST_CONV_F16X2 only — an activation left the fp16 operand range
+ *   (|x| >= 1023.75), the result of this call is invalid; re-run with VST_CONV_TF32X2. */
+#define VST_STATUS_F16_RANGE 1
 size_t vst_revnet_workspace_bytes(const vst_revnet* net, int B, int H, int W);
 
 /* encode: x [B,in_channel,H,W] -> z [B, 2*hidden_dim, H*2^sp/ds, W*2^sp/ds]
@@ -133,6 +138,22 @@ int vst_cwct_stats(const float* feat, int C, long long n, const uint8_t* labels,
 int vst_cwct_factor(const void* content_stats, const void* const* style_stats, const float* alpha_s,
                     int n_styles, float alpha_c, float eps, int C, int n_labels, int masked,
                     int use_double, float* T, float* mu, float* beta, int* valid, int* status, void* stream);
+
+/* The two halves of the transform as the reference exposes them (one label, unmasked):
+ *   vst_cwct_whiten_factor: T = Lc^-1, mu = mean, beta = 0   => apply gives whitening(x)       (cWCT.py:134-149)
+ *   vst_cwct_color_factor : T = Ls,    mu = 0,    beta = mean => apply gives coloring(w, style) (cWCT.py:152-164)
+ * `stats` is a one-label block of vst_cwct_stats over the tensor whose covariance is factorised. */
+int vst_cwct_whiten_factor(const void* stats, float eps, int C, int use_double, float* T, float* mu, float* beta,
+                           int* valid, int* status, void* stream);
+int vst_cwct_color_factor(const void* stats, float eps, int C, int use_double, float* T, float* mu, float* beta,
+                          int* valid, int* status, void* stream);
+
+/* cholesky_dec (cWCT.py:111-132) of a given C x C matrix on the device: L = chol(cov), on failure cov += eps*I,
+ * then 2 eps*I more, ... (cumulative); invert != 0 returns L^-1 (torch.inverse(L)).  cov / out are fp32
+ * (is_double == 0) or fp64 [C,C] row-major; only the lower triangle of cov is read; the strict upper triangle of
+ * out is zero.  status[0] = #retries, or -1 (out = NaN) if 64 retries did not help.  No host synchronisation. */
+int vst_cwct_cholesky(const void* cov, int C, int is_double, float eps, int invert, void* out, int* status,
+                      void* stream);
 
 /* out[:,p] = T[l(p)] (feat[:,p] - mu[l(p)]) + beta[l(p)]; labels NULL => l = 0; pixels whose
  * label has valid[l] == 0 are copied through.  `out` may alias `feat`.

@@ -4,7 +4,9 @@
 Same flags.  Differences: the style image is encoded and factorised once, not once per
 frame (video_transfer.py:195 is loop-invariant); under ``torchrun --nproc-per-node N`` the frames are
 rank-strided over N GPUs with one NCCL broadcast of the style statistics, and rank 0 writes the video in
-frame order.  ``--synthetic HxWxF`` stylizes F random frames without any input files.
+frame order from a shared-memory frame ring (vstnet_b200.video.SharedFrameRing).  ``--synthetic HxWxF``
+stylizes F random frames without any input files.  ``main`` returns the stylized uint8 RGB frames of this
+rank as ``{frame index: array}`` (single process: all of them).
 """
 import argparse
 import os
@@ -95,36 +97,77 @@ def main(argv=None):
 
     video_h, video_w = frames[0].shape[:2]
     mine = shard_frames(len(frames), rank, world)
-    out = {}
+    down = int(RevNetwork.down_scale)
 
     def host_frames():
         for i in mine:
             frame = Image.fromarray(frames[i])
-            frame = img_resize(frame, args.max_size, down_scale=RevNetwork.down_scale)  # ref :161
+            frame = img_resize(frame, args.max_size, down_scale=down)                   # ref :161
             yield torch.from_numpy(np.array(frame))
 
-    # pipelined host path: upload, n_streams frames in flight on the GPU, download (vstnet_b200/video.py)
-    for i, o in zip(mine, vs.stylize_stream(host_frames(), bgr=False)):
-        out[i] = o.clone().numpy()                                                     # RGB uint8 HWC
-    # gather frames on rank 0 in frame order (host side; no device collective on the data path)
-    if world > 1:
-        gathered = [None] * world
-        dist.gather_object(out, gathered if rank == 0 else None, dst=0)
-        if rank == 0:
-            out = {k: v for d in gathered for k, v in d.items()}
-    if rank == 0:
+    probe = img_resize(Image.fromarray(frames[0]), args.max_size, down_scale=down)
+    same_size = (probe.size[1], probe.size[0]) == (video_h, video_w)
+
+    def stylized_u8():
+        """Stylized uint8 RGB HWC frames of this rank, in order, at the VIDEO's size.  When the network ran at the
+        video's own size this is the pipelined uint8 path (vstnet_b200/video.py); otherwise the reference's order is
+        kept — resize the float result to the video size (torchvision bicubic), then quantise (ref :208-212)."""
+        if same_size:
+            yield from vs.stylize_stream(host_frames(), bgr=False)
+            return
+        from torchvision import transforms
+        to_video = transforms.Resize((video_h, video_w), interpolation=Image.BICUBIC)
+        for f in host_frames():
+            x = (f.to(device).permute(2, 0, 1)[None].float() / 255)
+            y = to_video(vs.stylize(x))
+            yield y[0].mul(255).clamp(0, 255).byte().permute(1, 2, 0).cpu()
+
+    def write_video(get_frame):
         import cv2
         path = os.path.join(args.out_dir, name)
         wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc('m', 'p', '4', 'v'), args.fps, (video_w, video_h))
         for i in range(len(frames)):
-            f = out[i]
-            if f.shape[0] != video_h or f.shape[1] != video_w:                          # ref :210 resize to video size
-                f = np.array(Image.fromarray(f).resize((video_w, video_h), Image.BICUBIC))
-            wr.write(np.ascontiguousarray(f[..., ::-1]))
+            wr.write(np.ascontiguousarray(get_frame(i)[..., ::-1]))
         wr.release()
         print("Save at %s" % path)
-    if world > 1:
+
+    if world == 1:
+        out = {}
+        for i, o in zip(mine, stylized_u8()):
+            out[i] = o.clone().numpy()
+        write_video(lambda i: out[i])
+        return out
+    else:
+        # ordered delivery through a bounded ring in shared host memory (no pickling, no device collective on the
+        # data path): every rank copies its frames in, rank 0's writer thread takes them out in frame order
+        import threading
+        from vstnet_b200.video import SharedFrameRing
+        tag = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+        path = SharedFrameRing.default_path(tag)
+        slots = 4 * world * vs.n_streams
+        if rank == 0:
+            ring = SharedFrameRing(path, (video_h, video_w, 3), slots, create=True)
+        dist.barrier()
+        if rank != 0:
+            ring = SharedFrameRing(path, (video_h, video_w, 3), slots, create=False)
+        writer, out = None, {}
+        if rank == 0:
+            def take(i):
+                if i > 0:
+                    ring.release(i - 1)
+                return ring.get(i)
+            writer = threading.Thread(target=write_video, args=(take,))
+            writer.start()
+        for i, o in zip(mine, stylized_u8()):
+            ring.put(i, o)
+            out[i] = o.clone().numpy()
+        if writer is not None:
+            writer.join()
+            ring.release(len(frames) - 1)
+        dist.barrier()
+        ring.close(unlink=(rank == 0))
         dist.destroy_process_group()
+        return out
 
 
 if __name__ == "__main__":

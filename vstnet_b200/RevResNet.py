@@ -103,7 +103,16 @@ class RevResNet(nn.Module):
         self.precision = precision
         self._packed = None
         self._packed_key = None
+        self._packed_event = None
+        self._packed_streams = set()
         self._ws = {}
+        # fp16 operand range guard of the f16x2 arithmetic (|activation| must stay below 1023.75; the reference's
+        # trained checkpoint produces |z| ~ 1.2, image_transfer.py:183-205).  The kernels raise a bit in the status word
+        # at the head of the workspace; "deferred" reads it back asynchronously and, when a LATER call finds it set,
+        # warns and switches this module to tf32x2 (fp32 exponent range) for good; "strict" synchronises after every
+        # call and transparently re-runs the flagged call in tf32x2; "off" skips the read-back.
+        self.range_check = "deferred"
+        self._range_pending = []
         n_params = sum(p.numel() for p in self.parameters())
         assert n_params == lib.vst_revnet_param_floats(h), "parameter layout mismatch with the native plan"
 
@@ -134,8 +143,14 @@ class RevResNet(nn.Module):
 
     # ------------------------------------------------------------------ device-side state
     def _packed_weights(self, device):
+        """The weights repacked into the kernels' layouts (device buffer, cached until a parameter changes).
+
+        Packing is asynchronous on the stream that first needs it; an event recorded behind the pack kernels is
+        waited on by every OTHER stream that uses the buffer (encode_pair's side stream, VideoStylizer's compute
+        streams), and the buffer is ``record_stream``'d for them so the allocator never recycles it under a reader."""
         params = list(self.state_dict(keep_vars=True).values())
         key = (str(device), self._precision) + tuple((p.data_ptr(), p._version) for p in params)
+        st = torch.cuda.current_stream(device)
         if key != self._packed_key:
             for p in params:
                 if p.device != device or p.dtype != torch.float32:
@@ -143,11 +158,17 @@ class RevResNet(nn.Module):
                                        % (device, p.dtype, p.device))
             flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
             packed = torch.empty(int(self._lib.vst_revnet_packed_bytes(self._h)) + 16, dtype=torch.uint8, device=device)
-            st = torch.cuda.current_stream(device)
             _lib.check(self._lib.vst_revnet_pack_weights(self._h, flat.data_ptr(), packed.data_ptr(), st.cuda_stream),
                        "vst_revnet_pack_weights")
             flat.record_stream(st)
+            ev = torch.cuda.Event()
+            ev.record(st)
             self._packed, self._packed_key = packed, key
+            self._packed_event, self._packed_streams = ev, {st.cuda_stream}
+        elif st.cuda_stream not in self._packed_streams:
+            st.wait_event(self._packed_event)          # ordered behind the pack kernels of the packing stream
+            self._packed.record_stream(st)
+            self._packed_streams.add(st.cuda_stream)
         return self._packed
 
     def _workspace(self, device, B, H, W):
@@ -187,6 +208,8 @@ class RevResNet(nn.Module):
         self._check_input(b, "b")
         dev = a.device
         cur = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            self._packed_weights(dev)                  # packed on `cur`, before the side stream forks from it
         side = self.__dict__.get("_side_stream")
         if side is None or side.device != dev:
             side = torch.cuda.Stream(dev)
@@ -198,6 +221,61 @@ class RevResNet(nn.Module):
         cur.wait_stream(side)
         zb.record_stream(cur)
         return za, zb
+
+    # ------------------------------------------------------------------ launch + range guard
+    def _range_fallback(self, when):
+        import warnings
+        warnings.warn("vstnet_b200.RevResNet: an activation exceeded the fp16 operand range of precision 'f16x2' "
+                      "(|x| >= 1023.75) %s; switching this module to precision 'tf32x2'" % when, RuntimeWarning)
+        self.precision = "tf32x2"
+
+    def _poll_range(self, block=False):
+        keep, hit = [], False
+        for ev, host in self._range_pending:
+            if block:
+                ev.synchronize()
+            if ev.query():
+                hit = hit or bool(int(host[0]) & 1)
+            else:
+                keep.append((ev, host))
+        self._range_pending = keep
+        return hit
+
+    def check_status(self):
+        """Synchronise on the status words of the earlier calls; True if one of them left the f16x2 range (the module
+        has then been switched to tf32x2)."""
+        hit = self._poll_range(block=True)
+        if hit and self._precision == "f16x2":
+            self._range_fallback("in an earlier call, whose result is invalid")
+        return hit
+
+    def _launch(self, fn, what, src, dst, B, H, W):
+        dev = src.device
+        with torch.cuda.device(dev):
+            while True:
+                packed, ws = self._packed_weights(dev), self._workspace(dev, B, H, W)
+                st = torch.cuda.current_stream(dev)
+                _lib.check(fn(self._h, packed.data_ptr(), src.data_ptr(), dst.data_ptr(), B, H, W, ws.data_ptr(),
+                              ws.numel(), st.cuda_stream), what)
+                if self._precision != "f16x2" or self.range_check == "off":
+                    return
+                if self._poll_range():
+                    self._range_fallback("in an earlier call, whose result is invalid")
+                    return
+                host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+                host.copy_(ws[:4].view(torch.int32), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                if self.range_check == "strict":
+                    ev.synchronize()
+                    if int(host[0]) & 1:
+                        self._range_fallback("in this call; re-running it")
+                        continue
+                    return
+                if len(self._range_pending) >= 16:
+                    self._range_pending.pop(0)
+                self._range_pending.append((ev, host))
+                return
 
     @torch.no_grad()
     def _forward(self, x):
@@ -212,11 +290,7 @@ class RevResNet(nn.Module):
         x = x.contiguous()
         f = 2 ** self.sp_steps
         z = torch.empty(B, self.latent_channels, H // ds * f, W // ds * f, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            packed, ws = self._packed_weights(x.device), self._workspace(x.device, B, H, W)
-            st = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(self._lib.vst_revnet_forward(self._h, packed.data_ptr(), x.data_ptr(), z.data_ptr(), B, H, W,
-                                                    ws.data_ptr(), ws.numel(), st), "vst_revnet_forward")
+        self._launch(self._lib.vst_revnet_forward, "vst_revnet_forward", x, z, B, H, W)
         return z
 
     @torch.no_grad()
@@ -230,9 +304,5 @@ class RevResNet(nn.Module):
         H, W = h // f * ds, w // f * ds
         z = z.contiguous()
         x = torch.empty(B, self.in_channel, H, W, dtype=torch.float32, device=z.device)
-        with torch.cuda.device(z.device):
-            packed, ws = self._packed_weights(z.device), self._workspace(z.device, B, H, W)
-            st = torch.cuda.current_stream(z.device).cuda_stream
-            _lib.check(self._lib.vst_revnet_inverse(self._h, packed.data_ptr(), z.data_ptr(), x.data_ptr(), B, H, W,
-                                                    ws.data_ptr(), ws.numel(), st), "vst_revnet_inverse")
+        self._launch(self._lib.vst_revnet_inverse, "vst_revnet_inverse", z, x, B, H, W)
         return x

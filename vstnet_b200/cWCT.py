@@ -45,6 +45,42 @@ class cWCT(nn.Module):
         self.use_double = use_double
         self._lib = _lib.load()
         self.last_status = None     # int32 [L] device tensor of the last call: #jitter retries per label
+        self._pending = []          # (event, pinned status copy) of earlier unmasked calls, checked without a sync
+        self._pin_ring = {}         # numpy mask staging: nbytes -> [slot index, [(pinned buffer, event), ...]]
+
+    # ------------------------------------------------------------------ deferred failure reporting
+    def _defer_status_check(self, status, stream):
+        """An unmasked call whose Cholesky never succeeded (status -1 after 64 jitter retries) returns the content
+        features unchanged.  The hot path must not synchronise, so the status words are copied to pinned memory
+        asynchronously and inspected at the start of a LATER call, once their event has completed: a warning then
+        names the failure.  ``check_status()`` inspects them now (synchronising)."""
+        if len(self._pending) >= 8:                      # never grows without bound: the oldest is simply dropped
+            self._pending.pop(0)
+        host = torch.empty(status.numel(), dtype=torch.int32, pin_memory=True)   # caching host allocator
+        host.copy_(status, non_blocking=True)            # on the current stream, after the factor kernel
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        self._pending.append((ev, host))
+
+    def _poll_status(self, block=False):
+        keep = []
+        for ev, host in self._pending:
+            if block:
+                ev.synchronize()
+            if ev.query():
+                if bool((host < 0).any()):
+                    import warnings
+                    warnings.warn("vstnet_b200.cWCT: a Cholesky factorisation did not succeed within 64 jitter retries; "
+                                  "that sample's content features were returned unstylized", RuntimeWarning)
+            else:
+                keep.append((ev, host))
+        self._pending = keep
+
+    def check_status(self):
+        """Synchronise on the earlier calls' status words and warn about failed factorisations; returns last_status
+        as a host list."""
+        self._poll_status(block=True)
+        return None if self.last_status is None else self.last_status.cpu().tolist()
 
     # ------------------------------------------------------------------ low-level steps
     def _stats(self, feat2d, C_, n, labels, L, stream):
@@ -67,6 +103,9 @@ class cWCT(nn.Module):
                                              beta.data_ptr(), valid.data_ptr(), status.data_ptr(), stream),
                    "vst_cwct_factor")
         self.last_status = status
+        if not masked:
+            self._poll_status()
+            self._defer_status_check(status, torch.cuda.current_stream(device))
         return T, mu, beta, valid
 
     def _apply(self, feat2d, out2d, C_, n, labels, L, T, mu, beta, valid, stream):
@@ -74,21 +113,28 @@ class cWCT(nn.Module):
                                             labels.data_ptr() if labels is not None else None, L, T.data_ptr(),
                                             mu.data_ptr(), beta.data_ptr(), valid.data_ptr(), stream), "vst_cwct_apply")
 
-    @staticmethod
-    def _mask_to_device(mask, n, device, what, hw=None):
-        """One sample's label map -> flat uint8 device tensor of n labels (+ its max label).  A 2-D map whose
-        size differs from the latent's ``hw = (H, W)`` is resized on the device, nearest neighbour with PIL's
+    def _mask_to_device(self, mask, n, device, what, hw=None):
+        """One sample's label map -> (flat uint8 device tensor of n labels, number of label slots L).
+
+        numpy masks (the reference's type) are staged through a small ring of pinned buffers and uploaded
+        asynchronously on the current stream; their maximum is taken on the host, so L = max+1 as in the
+        reference (cWCT.py:173-175) with no device synchronisation.  CUDA uint8 tensors are used in place and
+        sized L = 256 (every possible label gets a slot: nothing has to be read back).  A 2-D map whose size
+        differs from the latent's ``hw = (H, W)`` is resized on the device, nearest neighbour with PIL's
         sampling — the reference's ``cWCT.resize`` (cWCT.py:191-197), whose call this fork comments out
         (:72-73), so that there masks must already be at latent resolution (never true in artistic mode)."""
         if isinstance(mask, torch.Tensor):
             if mask.dtype != torch.uint8:
                 raise ValueError("%s must be uint8" % what)
-            m2 = mask.to(device)
+            if mask.is_cuda:
+                m2, L = mask.to(device), _lib.MAX_LABELS
+            else:
+                m2, L = self._upload(mask.contiguous(), device), int(mask.max()) + 1
         else:
             a = np.ascontiguousarray(np.asarray(mask))
             if a.dtype != np.uint8:
                 raise ValueError("%s must be uint8 (got %s)" % (what, a.dtype))
-            m2 = torch.from_numpy(a).to(device, non_blocking=False)
+            m2, L = self._upload(torch.from_numpy(a), device), int(a.max()) + 1
         if m2.numel() != n and hw is not None and m2.dim() == 2:
             src = m2.contiguous()
             dst = torch.empty(hw[0] * hw[1], dtype=torch.uint8, device=device)
@@ -103,7 +149,107 @@ class cWCT(nn.Module):
         if m.numel() != n:
             raise ValueError("%s has %d labels but the feature map has %d positions; masks must be 2-D label maps or "
                              "flat maps at latent resolution (ref: cWCT.py:72-73)" % (what, m.numel(), n))
-        return m, int(m.max().item())
+        return m, L
+
+    def _upload(self, host, device):
+        """Host uint8 tensor -> device, asynchronously on the current stream through a ring of 4 pinned buffers per
+        size (a pageable source would make the copy synchronous)."""
+        if host.is_pinned():
+            return host.to(device, non_blocking=True)
+        key = (host.numel(), str(device))
+        ring = self._pin_ring.setdefault(key, [0, []])
+        if len(ring[1]) < 4:
+            ring[1].append((torch.empty(host.numel(), dtype=torch.uint8, pin_memory=True), torch.cuda.Event()))
+            slot = len(ring[1]) - 1
+        else:
+            slot = ring[0] = (ring[0] + 1) % 4
+            ring[1][slot][1].synchronize()              # the upload that last used this buffer has completed
+        buf, ev = ring[1][slot]
+        buf.copy_(host.reshape(-1))
+        dev_t = torch.empty(host.shape, dtype=torch.uint8, device=device)
+        dev_t.view(-1).copy_(buf, non_blocking=True)
+        ev.record(torch.cuda.current_stream(device))
+        return dev_t
+
+    # ------------------------------------------------------------------ the reference's helper methods
+    def _factor_part(self, which, stats, C_, device, stream):
+        T = torch.empty(1, C_, C_, dtype=torch.float32, device=device)
+        mu = torch.empty(1, C_, dtype=torch.float32, device=device)
+        beta = torch.empty(1, C_, dtype=torch.float32, device=device)
+        valid = torch.empty(1, dtype=torch.int32, device=device)
+        status = torch.empty(1, dtype=torch.int32, device=device)
+        fn = self._lib.vst_cwct_whiten_factor if which == "whiten" else self._lib.vst_cwct_color_factor
+        _lib.check(fn(stats.data_ptr(), float(self.eps), C_, int(bool(self.use_double)), T.data_ptr(), mu.data_ptr(),
+                      beta.data_ptr(), valid.data_ptr(), status.data_ptr(), stream), "vst_cwct_%s_factor" % which)
+        self.last_status = status
+        return T, mu, beta, valid
+
+    @staticmethod
+    def _as_batches(x, what):
+        if not isinstance(x, torch.Tensor) or x.dim() not in (2, 3):
+            raise ValueError("%s must be [C,n] or [B,C,n]" % what)
+        if not x.is_cuda:
+            raise RuntimeError("vstnet_b200.cWCT runs on CUDA (sm_100a) only; %s is on %s — there is no CPU fallback"
+                               % (what, x.device))
+        if x.dtype != torch.float32:
+            raise ValueError("%s must be float32 (got %s)" % (what, x.dtype))
+        xb = x.contiguous()
+        return xb[None] if x.dim() == 2 else xb
+
+    @torch.no_grad()
+    def whitening(self, x):
+        """``inv(chol(cov(x))) @ (x - mean(x))`` for x ``[C,n]`` (ref: cWCT.py:134-149; the fork's version is 2-D
+        only, ``[B,C,n]`` is accepted here with the upstream per-sample meaning)."""
+        xb = self._as_batches(x, "x")
+        out = torch.empty_like(xb)
+        B, C_, n = xb.shape
+        with torch.cuda.device(xb.device):
+            st = torch.cuda.current_stream(xb.device).cuda_stream
+            for i in range(B):
+                stats = self._stats(xb[i], C_, n, None, 1, st)
+                T, mu, beta, valid = self._factor_part("whiten", stats, C_, xb.device, st)
+                self._apply(xb[i], out[i], C_, n, None, 1, T, mu, beta, valid, st)
+        return out[0] if x.dim() == 2 else out
+
+    @torch.no_grad()
+    def coloring(self, content_whiten_feat, style_feat):
+        """``chol(cov(style)) @ whiten + mean(style)`` (ref: cWCT.py:152-164)."""
+        wb, sb = self._as_batches(content_whiten_feat, "content_whiten_feat"), self._as_batches(style_feat, "style_feat")
+        if wb.shape[:2] != sb.shape[:2]:
+            raise ValueError("content and style features must agree in batch and channels")
+        out = torch.empty_like(wb)
+        B, C_, n = wb.shape
+        with torch.cuda.device(wb.device):
+            st = torch.cuda.current_stream(wb.device).cuda_stream
+            for i in range(B):
+                stats = self._stats(sb[i], C_, sb.shape[2], None, 1, st)
+                T, mu, beta, valid = self._factor_part("color", stats, C_, wb.device, st)
+                self._apply(wb[i], out[i], C_, n, None, 1, T, mu, beta, valid, st)
+        return out[0] if content_whiten_feat.dim() == 2 else out
+
+    @torch.no_grad()
+    def cholesky_dec(self, conv, invert=False):
+        """Cholesky factor of ``conv`` ``[C,C]`` with the cumulative ``eps*I`` retry, optionally inverted — on the
+        device, without the reference's exception / host round trip per retry (ref: cWCT.py:111-132)."""
+        if not isinstance(conv, torch.Tensor) or conv.dim() != 2 or conv.shape[0] != conv.shape[1]:
+            raise ValueError("conv must be a square matrix [C,C]")
+        if not conv.is_cuda:
+            raise RuntimeError("vstnet_b200.cWCT runs on CUDA (sm_100a) only; conv is on %s" % conv.device)
+        if conv.dtype not in (torch.float32, torch.float64):
+            raise ValueError("conv must be float32 or float64")
+        C_ = conv.shape[0]
+        if C_ > 128:
+            raise ValueError("vstnet_b200.cWCT supports at most 128 feature channels (got %d)" % C_)
+        a = conv.contiguous()
+        out = torch.empty_like(a)
+        status = torch.empty(1, dtype=torch.int32, device=a.device)
+        with torch.cuda.device(a.device):
+            st = torch.cuda.current_stream(a.device).cuda_stream
+            _lib.check(self._lib.vst_cwct_cholesky(a.data_ptr(), C_, int(a.dtype == torch.float64), float(self.eps),
+                                                   int(bool(invert)), out.data_ptr(), status.data_ptr(), st),
+                       "vst_cwct_cholesky")
+        self.last_status = status
+        return out
 
     # ------------------------------------------------------------------ reference API
     def transfer(self, content_feat, style_feat, cmask=None, smask=None):
@@ -146,12 +292,12 @@ class cWCT(nn.Module):
 
     # ------------------------------------------------------------------ style hoisting (video)
     @torch.no_grad()
-    def precompute_style(self, style_feat, smask=None):
+    def precompute_style(self, style_feat, smask=None, n_labels=None):
         """Style statistics computed once per video instead of once per frame (the reference
         re-encodes and re-factorises the style every frame, video_transfer.py:195).
 
-        Returns an opaque dict whose ``stats`` tensors (one uint8 device buffer per sample) can be
-        ``torch.distributed.broadcast`` to the other ranks as they are."""
+        Returns an opaque dict whose ``stats`` tensors (one uint8 device buffer per sample) are what
+        ``vstnet_b200.video.broadcast_style_stats`` sends to the other ranks."""
         _check_feat(style_feat, "style_feat")
         B, N, sH, sW = style_feat.shape
         dev = style_feat.device
@@ -162,7 +308,9 @@ class cWCT(nn.Module):
             st = torch.cuda.current_stream(dev).cuda_stream
             if smask is not None:
                 masks = [self._mask_to_device(smask[i], ns, dev, "smask", (sH, sW)) for i in range(B)]
-                L = min(max(mx for _, mx in masks) + 1, 255)
+                L = min(max(Li for _, Li in masks), _lib.MAX_LABELS)
+                if n_labels is not None:                # a fixed number of label slots (multi-GPU: every rank
+                    L = max(L, int(n_labels))           # knows the buffer size without communication)
             for i in range(B):
                 stats.append(self._stats(style[i], N, ns, masks[i][0] if smask is not None else None, L, st))
         return {"stats": stats, "L": L, "masked": smask is not None, "C": N}
@@ -212,13 +360,13 @@ class cWCT(nn.Module):
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             for i in range(B):
-                cm, cmax = self._mask_to_device(cmask[i], nc, dev, "cmask", (cH, cW))
+                cm, L = self._mask_to_device(cmask[i], nc, dev, "cmask", (cH, cW))
                 sm, _ = self._mask_to_device(smask[i], ns, dev, "smask", (sH, sW))
                 # the reference sizes its validity table max(content label)+1 (cWCT.py:173-175);
-                # label 255 overflows its uint8 arithmetic there and raises IndexError.
-                if cmax >= 255:
+                # label 255 overflows its uint8 arithmetic there and raises IndexError (host masks only:
+                # a device mask is never read back, label 255 is then an ordinary label).
+                if L > 255 and not (isinstance(cmask[i], torch.Tensor) and cmask[i].is_cuda):
                     raise IndexError("content label 255 is not supported (ref: cWCT.py:173 overflows uint8)")
-                L = cmax + 1
                 cst = self._stats(content_feat[i], N, nc, cm, L, st)
                 sst = self._stats(style[i], N, ns, sm, L, st)
                 T, mu, beta, valid = self._factor(cst, [sst], [1.0], 0.0, N, L, True, dev, st)

@@ -318,11 +318,8 @@ __global__ void __launch_bounds__(128, 3) rev_block16_kernel(Block16Args a) {
 }
 
 int launch_rev_block16(const Block16Args& a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(rev_block16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b16::SMEM));
-        attr_set = true;
-    }
+    static PerDeviceOnce smem_once;
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, rev_block16_kernel, (int)b16::SMEM));
     VST_REQUIRE(a.H >= 4 && a.W >= 4, "rev_block16: image too small (%dx%d)", a.H, a.W);
     VST_REQUIRE(a.b1 == a.w1 + 576 && a.w2 == a.b1 + 4 && a.b2 == a.w2 + 144 && a.w3 == a.b2 + 4 && a.b3 == a.w3 + 576 &&
                     ((uintptr_t)a.w1 & 15) == 0,

@@ -79,6 +79,7 @@ struct BlockTcArgs {
     float* out;            // P4
     const uint8_t* wpack;  // pack_block_tc_kernel output
     int H, W, sub;         // sub: 0 out = res + F(x), 1 out = res - F(x)
+    int* status;           // status word of the call (fp16 range guard), may be null
     int n_strips, rows_per_seg;
     long long* trace;      // developer aid (VST_TC_TRACE="1016,0" / "1064,0"): clock64 stamps of CTA trace_cta, 4096 per role
     int trace_cta;
@@ -199,13 +200,14 @@ __device__ __forceinline__ void btc_sts128(uint32_t addr, uint4 v) {
 }
 
 // 8 scaled fp32 values -> 16 bytes of fp16 hi and 16 bytes of fp16 lo
-__device__ __forceinline__ void btc_split8(const float* x, uint4& hv, uint4& lv) {
+__device__ __forceinline__ void btc_split8(const float* x, uint4& hv, uint4& lv, uint32_t& hmax) {
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
         const float2 hf = __half22float2(hh);
         hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        hmax = range_fold(hmax, hw[e]);
         lw[e] = btc_pack_half2(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
     }
     hv = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -227,6 +229,7 @@ struct BtcMidArgs {
     uint32_t tring, t_full, t_empty;
     uint32_t bias, exch;
     int nacc, nacc_log2, rows, bar_id, x0, W;
+    int* status;
     long long* trace;              // tracing builds: wait accounting of this role (nullptr otherwise)
 };
 template <int C>
@@ -241,6 +244,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     const uint32_t ex_r = g.exch + (uint32_t)(((q < 3 ? q + 1 : 3) * 2 + 1) * M * 4);          // right warp's lane 0, kx = 2
     const uint32_t trow = g.tacc + ((uint32_t)(q * 32) << 16);
     uint32_t par = 0;
+    uint32_t hmax = 0u;                         // fp16 range guard (tc_ptx.cuh)
     BTC_ACC_BEGIN();
 #pragma unroll 1
     for (int l = 0; l < g.rows; ++l) {
@@ -301,6 +305,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
                 if (M == 4) {
                     const __half2 h01 = __floats2half2_rn(o[0], o[1]), h23 = __floats2half2_rn(o[2], o[3]);
                     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    hmax = range_fold(range_fold(hmax, *reinterpret_cast<const uint32_t*>(&h01)), *reinterpret_cast<const uint32_t*>(&h23));
                     const uint4 v = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23),
                                                btc_pack_half2(o[0] - f01.x, o[1] - f01.y), btc_pack_half2(o[2] - f23.x, o[3] - f23.y));
                     if (own) btc_sts128(slot, v);
@@ -308,7 +313,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
                     if (mir_r) btc_sts128(slot + 32, v);
                 } else {
                     uint4 hv, lv;
-                    btc_split8(o, hv, lv);
+                    btc_split8(o, hv, lv, hmax);
                     const uint32_t ph = slot + ps * Cfg::CHUNK, pl = ph + Cfg::T_TERM;     // term 0 (hi) / term 1 (lo), K chunk ps
                     if (own) { btc_sts128(ph, hv); btc_sts128(pl, lv); }
                     if (mir_l) { btc_sts128(ph - 32, hv); btc_sts128(pl - 32, lv); }
@@ -320,6 +325,7 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
         fence_proxy_async();
         mbar_arrive_a(g.t_full + 8 * st);
     }
+    range_report(hmax, g.status);
     if (m == 0) BTC_ACC_END(g.trace, g.bar_id, g.rows);
 }
 
@@ -535,6 +541,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         const uint32_t bx_full = smem_u32(x_full), bx_empty = smem_u32(x_empty);
         int s = 0;
         uint32_t pe = 1;
+        uint32_t hmax = 0u;                                           // fp16 range guard (tc_ptx.cuh)
         constexpr int GB = G < 8 ? G : 8;                             // groups per batch of loads in flight
         constexpr int NBATCH = G / GB, ITEMS = NB * NBATCH;           // item = (block, batch) of one row
         // software pipeline: the next item (possibly of the next row) is requested before the current one is converted
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
 #pragma unroll
                 for (int k = 0; k < GB / 2; ++k) {
                     uint4 hv, lv;
-                    btc_split8(xs + 8 * k, hv, lv);
+                    btc_split8(xs + 8 * k, hv, lv, hmax);
                     btc_sts128(hi + (b * (GB / 2) + k) * Cfg::CHUNK, hv);
                     btc_sts128(hi + Cfg::XT + (b * (GB / 2) + k) * Cfg::CHUNK, lv);
                 }
@@ -586,6 +593,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
             if (m == 0) BTC_TRACE(1, 3 * (rx - sg.xa) + 2);
             if (++s == NX) { s = 0; pe ^= 1u; }
         }
+        range_report(hmax, a.status);
         if (m == 0) BTC_ACC_END((a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr, 3, sg.xb - sg.xa + 1);
     } else if (warp >= Cfg::W_E1) {
         // ================= E1 (warps 8-11) / E2 (warps 12-15) =================
@@ -604,6 +612,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         g.rows = second ? sg.t2b - sg.t2a + 1 : sg.t1b - sg.t1a + 1;
         g.bar_id = second ? 2 : 1;
         g.x0 = sg.x0; g.W = W;
+        g.status = a.status;
         g.trace = (a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr;
         btc_mid_epilogue<C>(g);
     } else {
@@ -813,12 +822,9 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
 template <int C>
 static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
     using Cfg = BtcCfg<C>;
-    static bool attr_set = false;
+    static PerDeviceOnce smem_once;
     auto kern = rev_block_tc_kernel<C>;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     a.n_strips = cdiv(a.W, Cfg::NB * Cfg::XO);
     int nseg = std::max(1, num_sms() / a.n_strips);
     a.rows_per_seg = cdiv(a.H, nseg);
@@ -834,12 +840,12 @@ static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
 }
 
 int launch_rev_block_tc(int C, const float* x, const float* res, float* out, const float* wpack, int H, int W, int sub,
-                        cudaStream_t st) {
+                        int* status, cudaStream_t st) {
     VST_REQUIRE(C == 16 || C == 64, "rev_block_tc: C = %d not supported", C);
     VST_REQUIRE(H >= 2 && W >= 4, "rev_block_tc: map %dx%d too small", H, W);
     BlockTcArgs a;
     a.x = x; a.res = res; a.out = out; a.wpack = reinterpret_cast<const uint8_t*>(wpack);
-    a.H = H; a.W = W; a.sub = sub; a.n_strips = 0; a.rows_per_seg = 0; a.trace = nullptr; a.trace_cta = 0;
+    a.H = H; a.W = W; a.sub = sub; a.status = status; a.n_strips = 0; a.rows_per_seg = 0; a.trace = nullptr; a.trace_cta = 0;
     return C == 16 ? launch_block_tc_cfg<16>(a, st) : launch_block_tc_cfg<64>(a, st);
 }
 

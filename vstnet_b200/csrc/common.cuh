@@ -48,6 +48,24 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 int num_sms();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: remember per device
+// (not per process) that it has been set, so a process that uses a second GPU opts in there too.
+struct PerDeviceOnce {
+    std::atomic<bool> done[64];
+    PerDeviceOnce() { for (auto& d : done) d.store(false, std::memory_order_relaxed); }
+};
+template <typename K>
+inline cudaError_t ensure_dyn_smem(PerDeviceOnce& once, K kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && once.done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && tracked) once.done[dev].store(true, std::memory_order_release);
+    return e;
+}
+
 // Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains, so that its
 // prologue (barrier init, TMEM allocation, weight / bias staging — nothing that depends on the predecessor's output)
 // overlaps the predecessor's tail.  Such a kernel MUST execute pdl_wait() before its first access to dependent memory.

@@ -148,12 +148,9 @@ __global__ void __launch_bounds__(256) conv3x3_ffma_kernel(ConvArgs a) {
 template <int S, int CO, int WC, int PT, int KC>
 static int launch_cfg(const ConvArgs& a, cudaStream_t st) {
     using Cfg = ConvCfg<S, CO, WC, PT, KC>;
-    static bool attr_set = false;
+    static PerDeviceOnce smem_once;
     auto kern = conv3x3_ffma_kernel<S, CO, WC, PT, KC>;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     dim3 grid(cdiv(a.Wout, Cfg::TW), cdiv(a.Hout, Cfg::TH), cdiv(a.Cout, Cfg::CT));
     char cls[40];
     snprintf(cls, sizeof(cls), "conv3x3_ffma %d>%d s%d", a.Cin, a.Cout, S);

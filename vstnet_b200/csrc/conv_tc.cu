@@ -454,12 +454,9 @@ static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
 template <int N, int R, int TERMS, bool HALF, bool SQZ>
 static int launch_tc_cfg2(const ConvArgs& a, cudaStream_t st) {
     using Cfg = TcCfg<N, R, TERMS, HALF>;
-    static bool attr_set = false;
+    static PerDeviceOnce smem_once;
     auto kern = conv3x3_tc_kernel<N, R, TERMS, HALF, SQZ>;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     TcTiles tl;
     tl.n_xt = cdiv(a.Wout, 128); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / N;
     tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
         // one item = 8 channels (two P4 groups) of one pixel: 32 bytes in, 16 (hi) + 16 (lo) bytes out
         const int ctid = tid - 256;
         uint32_t it = 0;
+        uint32_t hmax = 0u;                    // fp16 range guard (tc_ptx.cuh)
         for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
             for (int c = 0; c < n_chunks; ++c, ++it) {
                 const int s = it % NR, o = it % NO;
@@ -286,13 +287,18 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                     const float4 v = raw[(2 * kh + 1) * (ROWS * Cfg::RAW_PW) + rp];
                     const float x[8] = {u.x * VST_HALF_SCALE, u.y * VST_HALF_SCALE, u.z * VST_HALF_SCALE, u.w * VST_HALF_SCALE,
                                         v.x * VST_HALF_SCALE, v.y * VST_HALF_SCALE, v.z * VST_HALF_SCALE, v.w * VST_HALF_SCALE};
-                    float h[8], l[8];
+                    uint32_t hw[4];
+                    float l[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        h[e] = __half2float(__float2half_rn(x[e]));
-                        l[e] = x[e] - h[e];
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+                        const float2 hf = __half22float2(hh);
+                        hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                        hmax = range_fold(hmax, hw[e]);
+                        l[2 * e] = x[2 * e] - hf.x;
+                        l[2 * e + 1] = x[2 * e + 1] - hf.y;
                     }
-                    hi[i] = make_uint4(pack_half2(h[0], h[1]), pack_half2(h[2], h[3]), pack_half2(h[4], h[5]), pack_half2(h[6], h[7]));
+                    hi[i] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     if (Cfg::TA == 2)
                         lo[i] = make_uint4(pack_half2(l[0], l[1]), pack_half2(l[2], l[3]), pack_half2(l[4], l[5]), pack_half2(l[6], l[7]));
                 }
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                 if (ctid == 0) TCH_TRACE(2, it);
             }
         }
+        range_report(hmax, a.status);
     } else if (warp < 8) {
         // ================= epilogue: TMEM -> (lane-shifted sum over kx) -> ReLU -> P4 global =================
         // lane l of warp (q, half) owns tile pixel m = 32q + l and the cout half `half`.
@@ -313,6 +320,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
         const int H = a.Hout, W = a.Wout, Wp = W + 2;
         const size_t plane = p4_plane_px(H, W);
         uint32_t tcount = 0;
+        uint32_t hmax = 0u;                    // fp16 range guard of the H8 output (tc_ptx.cuh)
         for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
             const int ct = t % tl.n_ct, rest = t / tl.n_ct;
             const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * R;
@@ -359,6 +367,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                                 const __half2 hh = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
                                 const float2 hf = __half22float2(hh);
                                 hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                                hmax = range_fold(hmax, hw[e]);
                                 lw[e] = pack_half2(o[2 * e] - hf.x, o[2 * e + 1] - hf.y);
                             }
                             const uint4 hv = make_uint4(hw[0], hw[1], hw[2], hw[3]), lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -420,6 +429,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
             mbar_arrive(&acc_empty[b]);
             if (tid == 0) TCH_TRACE(7, 2 * tcount + 1);
         }
+        if (SPLIT) range_report(hmax, a.status);
     }
 
     tc_fence_before();
@@ -439,12 +449,9 @@ static int launch_tch_cfg(const ConvArgs& a, cudaStream_t st) {
 template <int NC, int R, int TERMS, bool SPLIT>
 static int launch_tch_cfg2(const ConvArgs& a, cudaStream_t st) {
     using Cfg = TchCfg<NC, R, TERMS>;
-    static bool attr_set = false;
+    static PerDeviceOnce smem_once;
     auto kern = conv3x3_tch_kernel<NC, R, TERMS, SPLIT>;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     TchTiles tl;
     tl.n_xt = cdiv(a.Wout, Cfg::XS); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / NC;
     tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;

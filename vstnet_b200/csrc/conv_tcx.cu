@@ -335,12 +335,9 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
 template <int NC, int R, int TERMS>
 static int launch_tcx_cfg(const ConvArgs& a, cudaStream_t st) {
     using Cfg = TcxCfg<NC, R, TERMS>;
-    static bool attr_set = false;
+    static PerDeviceOnce smem_once;
     auto kern = conv3x3_tcx_kernel<NC, R, TERMS>;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     TcxTiles tl;
     tl.n_xt = cdiv(a.Wout, Cfg::XS); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / NC;
     tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;

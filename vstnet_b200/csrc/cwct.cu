@@ -274,6 +274,8 @@ struct FactorArgs {
     int n_styles;
     float alpha_c, eps;
     int C, L, masked, use_double;
+    int mode;                    // 0: T = Mix Lc^-1 (transfer)   1: T = Lc^-1, beta = 0 (whitening, cWCT.py:134-149)
+                                 // 2: T = Mix, mu = 0, beta = mixed style mean (coloring, cWCT.py:152-164)
     float *T, *mu, *beta;
     int *valid, *status;
 };
@@ -293,7 +295,10 @@ __device__ void build_cov(double* A, const StatsView& sv, int l, int C, double n
         double g = 0.5 * (G[(size_t)i * C + j] + G[(size_t)j * C + i]);
         double c = (g - s[i] * s[j] / n) / (n - 1.0);
         if (round32) c = (double)(float)c;          // the reference's covariance is an fp32 matrix
-        if (i == j) c += jitter;
+        if (i == j) {
+            c += jitter;
+            if (round32) c = (double)(float)c;      // ... and conv + iden * eps an fp32 sum (cWCT.py:123)
+        }
         A[e] = c;
     }
 }
@@ -340,6 +345,8 @@ __device__ int chol_retry(double* A, const StatsView& sv, int l, int C, double n
         // noise of either sign; the reference (fp32 LAPACK on an fp32 matrix) sees noise ~1e-8 *
         // |diag|.  Make the outcome deterministic: a pivot below that noise floor is a failure.
         if (cholesky_packed(A, C, flag)) {
+            // fp64 factor arithmetic (use_double): torch.linalg.cholesky in fp64 accepts any positive pivot, so do we
+            if (!round32) return k;
             __shared__ int bad;
             if (threadIdx.x == 0) bad = 0;
             __syncthreads();
@@ -371,29 +378,36 @@ __global__ void __launch_bounds__(256) factor_kernel(FactorArgs fa) {
     __shared__ int flag;
     __shared__ int ok_s;
 
+    const bool has_c = fa.mode != 2, has_s = fa.mode != 1;
     const StatsView cs = stats_view(const_cast<void*>(fa.cstats), C, L);
-    const double nc = cs.count[l];
+    const double nc = has_c ? cs.count[l] : 2.0;
     float* T = fa.T + (size_t)l * C * C;
 
     bool ok = nc >= 2.0;
-    for (int k = 0; k < fa.n_styles && ok; ++k) {
+    for (int k = 0; has_s && k < fa.n_styles && ok; ++k) {
         const double ns = stats_view(const_cast<void*>(fa.sstats[k]), C, L).count[l];
         ok = ns >= 2.0;
         if (fa.masked)   // cWCT.py:178
             ok = ok && nc > 10.0 && ns > 10.0 && nc / ns < 100.0 && ns / nc < 100.0;
     }
     int retries = 0;
-    if (ok) {
+    if (ok && has_c) {
         int r = chol_retry(Lc, cs, l, C, nc, (double)fa.eps, !fa.use_double, &flag);
         if (r < 0) ok = false; else retries += r;
     }
-    for (int e = threadIdx.x; e < TRI; e += blockDim.x) Mix[e] = 0.0;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        mu_c[i] = ok ? (double)cs.pivot[i] + cs.sum[(size_t)l * C + i] / nc : 0.0;
-        mu_m[i] = 0.0;
+    for (int e = threadIdx.x; e < TRI; e += blockDim.x) {
+        Mix[e] = 0.0;
+        if (!has_c) Lc[e] = 0.0;
     }
     __syncthreads();
-    for (int k = 0; k < fa.n_styles && ok; ++k) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        mu_c[i] = (ok && has_c) ? (double)cs.pivot[i] + cs.sum[(size_t)l * C + i] / nc : 0.0;
+        mu_m[i] = 0.0;
+        if (!has_c) Lc[tri(i, i)] = 1.0;          // coloring only: Lc = I
+        if (!has_s) Mix[tri(i, i)] = 1.0;         // whitening only: Mix = I
+    }
+    __syncthreads();
+    for (int k = 0; has_s && k < fa.n_styles && ok; ++k) {
         const StatsView ss = stats_view(const_cast<void*>(fa.sstats[k]), C, L);
         const double ns = ss.count[l];
         int r = chol_retry(Ls, ss, l, C, ns, (double)fa.eps, !fa.use_double, &flag);
@@ -443,6 +457,69 @@ __global__ void __launch_bounds__(256) factor_kernel(FactorArgs fa) {
         fa.valid[l] = ok ? 1 : 0;
         fa.status[l] = ok ? retries : ((nc >= 2.0 && !fa.masked) ? -1 : 0);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// cholesky_dec of a given C x C matrix (cWCT.py:111-132): L = chol(cov) with the cumulative eps*I retry,
+// optionally inverted (torch.inverse(L): forward substitution, column per thread).  One CTA.
+// ------------------------------------------------------------------------------------------
+template <typename TIO>
+__global__ void __launch_bounds__(256) cholesky_dec_kernel(const TIO* __restrict__ cov, int C, double eps, int invert,
+                                                           int round32, TIO* __restrict__ out, int* __restrict__ status) {
+    extern __shared__ __align__(16) double sm[];
+    const int TRI = C * (C + 1) / 2;
+    double* A = sm;              // packed lower factor
+    double* X = sm + TRI;        // packed lower inverse
+    __shared__ int flag;
+    __shared__ int bad;
+    int k = 0;
+    for (; k <= 64; ++k) {
+        __syncthreads();
+        if (threadIdx.x == 0) { flag = 0; bad = 0; }
+        const double jit = eps * (double)(k * (k + 1) / 2);
+        for (int e = threadIdx.x; e < TRI; e += blockDim.x) {
+            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (tri(i + 1, 0) <= e) ++i;
+            while (tri(i, 0) > e) --i;
+            const int j = e - tri(i, 0);
+            double c = (double)cov[(size_t)i * C + j];     // potrf reads the lower triangle
+            if (i == j) {
+                c += jit;
+                if (round32) c = (double)(float)c;         // conv + iden * eps is an fp32 sum in the reference
+            }
+            A[e] = c;
+        }
+        __syncthreads();
+        if (!cholesky_packed(A, C, &flag)) continue;
+        if (!round32) break;
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            const double cii = (double)cov[(size_t)i * C + i] + jit, lii = A[tri(i, i)];
+            if (!(lii * lii > 1e-7 * cii)) bad = 1;
+        }
+        __syncthreads();
+        if (!bad) break;
+    }
+    const bool ok = k <= 64;
+    __syncthreads();
+    if (ok && invert) {
+        // column j of X = L^-1: X[j][j] = 1 / L[j][j];  X[i][j] = -(sum_{m=j..i-1} L[i][m] X[m][j]) / L[i][i]
+        for (int j = threadIdx.x; j < C; j += blockDim.x) {
+            X[tri(j, j)] = 1.0 / A[tri(j, j)];
+            for (int i = j + 1; i < C; ++i) {
+                double s = 0.0;
+                for (int m = j; m < i; ++m) s += A[tri(i, m)] * X[tri(m, j)];
+                X[tri(i, j)] = -s / A[tri(i, i)];
+            }
+        }
+        __syncthreads();
+    }
+    const double* R = (ok && invert) ? X : A;
+    for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
+        const int i = e / C, j = e - i * C;
+        double v = ok ? (j <= i ? R[tri(i, j)] : 0.0) : nan("");
+        out[e] = (TIO)v;
+    }
+    if (threadIdx.x == 0) *status = ok ? k : -1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -600,12 +677,9 @@ template <int CP>
 static int launch_apply(const float* feat, float* out, int C, long long n, const uint8_t* labels, int L, const float* T,
                         const float* mu, const float* beta, const int* valid, cudaStream_t st) {
     using Cfg = ApplyCfg<CP>;
-    static bool attr_set = false;
+    static PerDeviceOnce smem_once;
     auto kern = apply_kernel<CP>;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     long long tiles = (n + Cfg::PX - 1) / Cfg::PX;
     int grid = (int)std::min<long long>(tiles, (long long)num_sms() * (CP == 32 ? 6 : 2));
     ProfScope prof(st, CP == 32 ? "cwct_apply c32" : "cwct_apply c128", 2.0 * C * C * (double)n,
@@ -661,34 +735,72 @@ extern "C" int vst_cwct_stats(const float* feat, int C, long long n, const uint8
     return check_launch("cwct_gram");
 }
 
-extern "C" int vst_cwct_factor(const void* content_stats, const void* const* style_stats, const float* alpha_s,
-                               int n_styles, float alpha_c, float eps, int C, int n_labels, int masked, int use_double,
-                               float* T, float* mu, float* beta, int* valid, int* status, void* stream) {
-    VST_REQUIRE(content_stats && style_stats && alpha_s && T && mu && beta && valid && status,
-                "vst_cwct_factor: null argument");
+static int launch_factor(int mode, const void* content_stats, const void* const* style_stats, const float* alpha_s,
+                         int n_styles, float alpha_c, float eps, int C, int n_labels, int masked, int use_double, float* T,
+                         float* mu, float* beta, int* valid, int* status, cudaStream_t st) {
+    VST_REQUIRE(T && mu && beta && valid && status, "vst_cwct_factor: null output");
+    VST_REQUIRE(mode == 2 || content_stats, "vst_cwct_factor: null content statistics");
+    VST_REQUIRE(mode == 1 || (style_stats && alpha_s), "vst_cwct_factor: null style statistics");
     VST_REQUIRE(C >= 1 && C <= 128, "cWCT supports 1 <= C <= 128 channels (got %d)", C);
-    VST_REQUIRE(n_styles >= 1 && n_styles <= VST_MAX_STYLES, "n_styles %d out of range", n_styles);
+    VST_REQUIRE(mode == 1 || (n_styles >= 1 && n_styles <= VST_MAX_STYLES), "n_styles %d out of range", n_styles);
     VST_REQUIRE(n_labels >= 1 && n_labels <= VST_MAX_LABELS, "n_labels %d out of range", n_labels);
     VST_REQUIRE(!masked || n_styles == 1, "masked transfer takes exactly one style (cWCT.py:49)");
     FactorArgs fa;
     fa.cstats = content_stats;
-    for (int k = 0; k < n_styles; ++k) {
+    fa.n_styles = mode == 1 ? 0 : n_styles;
+    for (int k = 0; k < fa.n_styles; ++k) {
         VST_REQUIRE(style_stats[k], "style_stats[%d] is null", k);
         fa.sstats[k] = style_stats[k];
         fa.alpha_s[k] = alpha_s[k];
     }
-    fa.n_styles = n_styles; fa.alpha_c = alpha_c; fa.eps = eps;
-    fa.C = C; fa.L = n_labels; fa.masked = masked; fa.use_double = use_double;
+    fa.alpha_c = alpha_c; fa.eps = eps;
+    fa.C = C; fa.L = n_labels; fa.masked = masked; fa.use_double = use_double; fa.mode = mode;
     fa.T = T; fa.mu = mu; fa.beta = beta; fa.valid = valid; fa.status = status;
     const size_t smem = ((size_t)3 * (C * (C + 1) / 2) + 2 * C) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (128 * 129 / 2) * 8 + 2 * 128 * 8));
-        attr_set = true;
-    }
-    ProfScope prof((cudaStream_t)stream, "cwct_factor", 0.0, 0.0);
-    factor_kernel<<<n_labels, 256, smem, (cudaStream_t)stream>>>(fa);
+    static PerDeviceOnce smem_once;
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, factor_kernel, 3 * (128 * 129 / 2) * 8 + 2 * 128 * 8));
+    ProfScope prof(st, "cwct_factor", 0.0, 0.0);
+    factor_kernel<<<n_labels, 256, smem, st>>>(fa);
     return check_launch("cwct_factor");
+}
+
+extern "C" int vst_cwct_factor(const void* content_stats, const void* const* style_stats, const float* alpha_s,
+                               int n_styles, float alpha_c, float eps, int C, int n_labels, int masked, int use_double,
+                               float* T, float* mu, float* beta, int* valid, int* status, void* stream) {
+    return launch_factor(0, content_stats, style_stats, alpha_s, n_styles, alpha_c, eps, C, n_labels, masked, use_double, T,
+                         mu, beta, valid, status, (cudaStream_t)stream);
+}
+
+extern "C" int vst_cwct_whiten_factor(const void* stats, float eps, int C, int use_double, float* T, float* mu, float* beta,
+                                      int* valid, int* status, void* stream) {
+    return launch_factor(1, stats, nullptr, nullptr, 0, 0.f, eps, C, 1, 0, use_double, T, mu, beta, valid, status,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int vst_cwct_color_factor(const void* stats, float eps, int C, int use_double, float* T, float* mu, float* beta,
+                                     int* valid, int* status, void* stream) {
+    const void* ss[1] = {stats};
+    const float one[1] = {1.f};
+    return launch_factor(2, nullptr, ss, one, 1, 0.f, eps, C, 1, 0, use_double, T, mu, beta, valid, status,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int vst_cwct_cholesky(const void* cov, int C, int is_double, float eps, int invert, void* out, int* status,
+                                 void* stream) {
+    VST_REQUIRE(cov && out && status, "vst_cwct_cholesky: null argument");
+    VST_REQUIRE(C >= 1 && C <= 128, "cWCT supports 1 <= C <= 128 channels (got %d)", C);
+    const size_t smem = (size_t)2 * (C * (C + 1) / 2) * sizeof(double);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_double) {
+        static PerDeviceOnce once;
+        VST_CUDA_OK(ensure_dyn_smem(once, cholesky_dec_kernel<double>, 2 * (128 * 129 / 2) * 8));
+        cholesky_dec_kernel<double><<<1, 256, smem, st>>>((const double*)cov, C, (double)eps, invert, 0, (double*)out, status);
+    } else {
+        static PerDeviceOnce once;
+        VST_CUDA_OK(ensure_dyn_smem(once, cholesky_dec_kernel<float>, 2 * (128 * 129 / 2) * 8));
+        cholesky_dec_kernel<float><<<1, 256, smem, st>>>((const float*)cov, C, (double)eps, invert, 1, (float*)out, status);
+    }
+    return check_launch("cwct_cholesky");
 }
 
 extern "C" int vst_cwct_apply(const float* feat, float* out, int C, long long n, const uint8_t* labels, int n_labels,

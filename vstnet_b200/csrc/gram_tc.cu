@@ -194,12 +194,9 @@ __global__ void __launch_bounds__(gtc::THREADS, 1) gram_tc_kernel(GramTcArgs a) 
 
 template <int SEGS>
 static int launch_gram_tc_cfg(const GramTcArgs& a0, cudaStream_t st) {
-    static bool attr_set = false;
+    static PerDeviceOnce smem_once;
     auto kern = gram_tc_kernel<SEGS>;
-    if (!attr_set) {
-        VST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gtc::SMEM));
-        attr_set = true;
-    }
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)gtc::SMEM));
     GramTcArgs a = a0;
     const long long run = (long long)SEGS * gtc::KT;
     const long long runs = (a.n + run - 1) / run;

@@ -49,6 +49,7 @@ __device__ __forceinline__ void p4_store(float4* plane, int H, int W, int y, int
 #endif
 
 #define VST_HALF_SCALE 64.0f
+// VST_STATUS_F16_RANGE (vstb200.h): some |VST_HALF_SCALE * x| rounded to +-inf in fp16 (|x| >= 1023.75)
 
 enum ConvEpi {
     EPI_RELU = 0,       // out = relu(conv + bias)
@@ -68,6 +69,7 @@ struct ConvArgs {
     int Cin, Cout, CoutPad, Hin, Win, Hout, Wout;
     int epi;
     int out_split;      // conv_tch only: write the result as split fp16 (hi planes, then lo planes; see below)
+    int* status;        // device status word of the call (bit 0: fp16 operand range exceeded), may be null
 };
 
 // "H8" split-half layout of a bottleneck tensor that only feeds a tensor-core conv (precision f16x2):
@@ -149,7 +151,7 @@ size_t block_tc_pack_floats(int C);
 int launch_pack_block_tc(int C, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                          const float* b3, float* pk, cudaStream_t st);
 int launch_rev_block_tc(int C, const float* x, const float* res, float* out, const float* wpack, int H, int W, int sub,
-                        cudaStream_t st);
+                        int* status, cudaStream_t st);
 
 // tensor-core (tcgen05) path, conv_tc.cu
 bool tc_eligible(int Cin, int Cout, int stride);
@@ -181,12 +183,12 @@ int launch_gram_tc(const float* feat, const float* pivot, double* count, double*
                    cudaStream_t st);
 
 // layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
-int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st);   // NCHW -> P4
+int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, cudaStream_t st);   // NCHW -> P4
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st);           // P4 -> NCHW
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st);
 int launch_p4_replicate_topleft(float* t, int C, int H, int W, cudaStream_t st);
 int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Win, cudaStream_t st);
 int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st);
-int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, cudaStream_t st);
+int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, int* status_clear, cudaStream_t st);
 
 }  // namespace vst

@@ -13,7 +13,8 @@ static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 
 // channels, channels >= Cimg zero.        injective_pad.inverse (:30-31): first Cimg channels of s0.
 // ------------------------------------------------------------------------------------------
 __global__ void image_to_state_kernel(const float* __restrict__ x, float4* __restrict__ s0, int Cimg, int G, int H,
-                                      int W) {
+                                      int W, int* __restrict__ status_clear) {
+    if (status_clear && blockIdx.x == 0 && threadIdx.x == 0) *status_clear = 0;     // first kernel of an encode
     const size_t n = (size_t)H * W, total = (size_t)G * n;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int g = (int)(i / n);
@@ -39,10 +40,10 @@ __global__ void state_to_image_kernel(const float4* __restrict__ s0, float* __re
     }
 }
 
-int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, cudaStream_t st) {
+int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, cudaStream_t st) {
     const size_t total = (size_t)(C0 / 4) * H * W;
     ProfScope prof(st, "image_to_state", 0.0, 4.0 * Cimg * H * W + 16.0 * total);
-    image_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(x, reinterpret_cast<float4*>(s0), Cimg, C0 / 4, H, W);
+    image_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(x, reinterpret_cast<float4*>(s0), Cimg, C0 / 4, H, W, status_clear);
     return check_launch("image_to_state");
 }
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st) {
@@ -132,7 +133,8 @@ int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Wi
 // ------------------------------------------------------------------------------------------
 template <int L, bool TO_LATENT>
 __global__ void latent_spread_kernel(float4* __restrict__ x1, float4* __restrict__ x2, float* __restrict__ z, int Ch,
-                                     int h, int w) {
+                                     int h, int w, int* __restrict__ status_clear) {
+    if (status_clear && blockIdx.x == 0 && threadIdx.x == 0) *status_clear = 0;     // first kernel of a decode
     constexpr int S = 1 << L;                               // sub-positions per axis
     const int Gh = Ch / 4, Cz = (2 * Ch) >> (2 * L), Gz = Cz / 4;
     const int H = h << L, W = w << L;
@@ -194,7 +196,8 @@ __global__ void latent_spread_kernel(float4* __restrict__ x1, float4* __restrict
 // any other depth (not used by the reference's two modes): one 4-channel unit per thread
 template <bool TO_LATENT>
 __global__ void latent_spread_generic_kernel(float4* __restrict__ x1, float4* __restrict__ x2, float* __restrict__ z,
-                                             int Ch, int h, int w, int L) {
+                                             int Ch, int h, int w, int L, int* __restrict__ status_clear) {
+    if (status_clear && blockIdx.x == 0 && threadIdx.x == 0) *status_clear = 0;
     const int Gh = Ch / 4;
     const size_t n = (size_t)h * w, total = (size_t)2 * Gh * n;
     const int H = h << L, W = w << L;
@@ -223,21 +226,22 @@ __global__ void latent_spread_generic_kernel(float4* __restrict__ x1, float4* __
 }
 
 template <bool TO_LATENT>
-static int launch_spread_any(float* x1, float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st) {
+static int launch_spread_any(float* x1, float* x2, float* z, int Ch, int h, int w, int L, int* status_clear, cudaStream_t st) {
     const size_t units = (size_t)2 * Ch * h * w / 4;
     float4 *a = reinterpret_cast<float4*>(x1), *b = reinterpret_cast<float4*>(x2);
     ProfScope prof(st, TO_LATENT ? "latent_spread" : "latent_gather", 0.0, 32.0 * units);
-    if (L == 2) latent_spread_kernel<2, TO_LATENT><<<ew_grid(units / 4), 256, 0, st>>>(a, b, z, Ch, h, w);
-    else if (L == 1) latent_spread_kernel<1, TO_LATENT><<<ew_grid(units / 2), 256, 0, st>>>(a, b, z, Ch, h, w);
-    else latent_spread_generic_kernel<TO_LATENT><<<ew_grid(units), 256, 0, st>>>(a, b, z, Ch, h, w, L);
+    if (L == 2) latent_spread_kernel<2, TO_LATENT><<<ew_grid(units / 4), 256, 0, st>>>(a, b, z, Ch, h, w, status_clear);
+    else if (L == 1) latent_spread_kernel<1, TO_LATENT><<<ew_grid(units / 2), 256, 0, st>>>(a, b, z, Ch, h, w, status_clear);
+    else latent_spread_generic_kernel<TO_LATENT><<<ew_grid(units), 256, 0, st>>>(a, b, z, Ch, h, w, L, status_clear);
     return check_launch(TO_LATENT ? "latent_spread" : "latent_gather");
 }
 
 int launch_latent_spread(const float* x1, const float* x2, float* z, int Ch, int h, int w, int L, cudaStream_t st) {
-    return launch_spread_any<true>(const_cast<float*>(x1), const_cast<float*>(x2), z, Ch, h, w, L, st);
+    return launch_spread_any<true>(const_cast<float*>(x1), const_cast<float*>(x2), z, Ch, h, w, L, nullptr, st);
 }
-int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, cudaStream_t st) {
-    return launch_spread_any<false>(x1, x2, const_cast<float*>(z), Ch, h, w, L, st);
+int launch_latent_gather(const float* z, float* x1, float* x2, int Ch, int h, int w, int L, int* status_clear,
+                         cudaStream_t st) {
+    return launch_spread_any<false>(x1, x2, const_cast<float*>(z), Ch, h, w, L, status_clear, st);
 }
 
 // ------------------------------------------------------------------------------------------

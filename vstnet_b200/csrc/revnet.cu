@@ -90,10 +90,12 @@ static bool block_fused_tc(const vst_revnet* n, const BlockDesc& b) {
 struct Shape { int c, h, w; };
 
 struct Workspace {
+    int* status;     // first 64 bytes of the workspace: [0] status bits of the last call (VST_STATUS_*)
     float* P[3];
     float* T1;
     float* T2;
 };
+constexpr size_t WS_HEADER_FLOATS = 16;
 
 static size_t half_state_floats(const vst_revnet* n, int H, int W) {
     // largest half-state over all stages, in the P4 layout (border + slack included)
@@ -120,10 +122,11 @@ static size_t temp_floats(const vst_revnet* n, int H, int W) {
 
 static int carve(const vst_revnet* n, int H, int W, void* ws, size_t ws_bytes, Workspace* out) {
     size_t hs = half_state_floats(n, H, W), ts = temp_floats(n, H, W);
-    size_t need = (3 * hs + 2 * ts) * sizeof(float);
+    size_t need = (WS_HEADER_FLOATS + 3 * hs + 2 * ts) * sizeof(float);
     VST_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: have %zu bytes, need %zu", ws_bytes, need);
     VST_REQUIRE(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
     float* p = (float*)ws;
+    out->status = (int*)p; p += WS_HEADER_FLOATS;
     for (int i = 0; i < 3; ++i) { out->P[i] = p; p += hs; }
     out->T1 = p; p += ts;
     out->T2 = p;
@@ -131,13 +134,14 @@ static int carve(const vst_revnet* n, int H, int W, void* ws, size_t ws_bytes, W
 }
 
 static ConvArgs conv_args(const ConvDesc& c, const float* packed, const float* in, int Hin, int Win, float* out,
-                          const float* res, int epi) {
+                          const float* res, int epi, int* status) {
     ConvArgs a;
     a.in = in; a.w = packed + c.pk_w; a.bias = packed + c.pk_b; a.res = res; a.out = out;
     a.Cin = c.Cin; a.Cout = c.Cout; a.CoutPad = c.CoutPad;
     a.Hin = Hin; a.Win = Win; a.Hout = Hin / c.stride; a.Wout = Win / c.stride;
     a.epi = epi;
     a.out_split = 0;
+    a.status = status;
     return a;
 }
 
@@ -153,8 +157,9 @@ static int tc_terms(int precision) {
 }
 
 static int run_conv(const vst_revnet* n, const ConvDesc& c, const float* packed, const float* in, int Hin, int Win,
-                    float* out, const float* res, int epi, cudaStream_t st, bool out_split = false, bool in_split = false) {
-    ConvArgs a = conv_args(c, packed, in, Hin, Win, out, res, epi);
+                    float* out, const float* res, int epi, int* status, cudaStream_t st, bool out_split = false,
+                    bool in_split = false) {
+    ConvArgs a = conv_args(c, packed, in, Hin, Win, out, res, epi, status);
     const int terms = tc_terms(n->precision);
     a.out_split = out_split ? 1 : 0;
     if (in_split) {
@@ -187,7 +192,7 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
                  const float* x_sq = nullptr) {
     const int Ho = Hin / b.stride, Wo = Win / b.stride;
     if (block_fused_tc(n, b) && (epi == EPI_ADD || epi == EPI_SUB) && Win >= 4)
-        return launch_rev_block_tc(b.channel, x, res, out, packed + b.pk_blk, Hin, Win, epi == EPI_SUB ? 1 : 0, st);
+        return launch_rev_block_tc(b.channel, x, res, out, packed + b.pk_blk, Hin, Win, epi == EPI_SUB ? 1 : 0, ws.status, st);
     if (b.stride == 1 && b.conv[0].Cin == 16 && b.conv[0].Cout == 4 && b.conv[2].Cout == 16 &&
         (epi == EPI_ADD || epi == EPI_SUB)) {
         // full-resolution stage: the whole block in one fused CUDA-core kernel (block16.cu)
@@ -201,22 +206,22 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
     }
     if (x_sq && block_s2tc(n, b)) {
         const ConvDesc& c = b.conv[0];
-        ConvArgs a = conv_args(c, packed, x_sq, Ho, Wo, ws.T1, nullptr, EPI_RELU);
+        ConvArgs a = conv_args(c, packed, x_sq, Ho, Wo, ws.T1, nullptr, EPI_RELU, ws.status);
         a.Cin = 4 * c.Cin; a.Hout = Ho; a.Wout = Wo;           // stride-1 conv on the squeezed tensor
         a.w = packed + c.pk_s2;
         if (launch_conv3x3_tch(a, 2, st)) return 1;
-    } else if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, st)) return 1;
+    } else if (run_conv(n, b.conv[0], packed, x, Hin, Win, ws.T1, nullptr, EPI_RELU, ws.status, st)) return 1;
     const bool split = block_split_t2(n, b);
-    if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, st, split, false)) return 1;
-    if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, st, false, split)) return 1;
+    if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, ws.status, st, split, false)) return 1;
+    if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, ws.status, st, false, split)) return 1;
     return 0;
 }
 
 static int forward_one(const vst_revnet* n, const float* packed, const float* x, float* z, int H, int W,
-                       const Workspace& ws, cudaStream_t st) {
+                       const Workspace& ws, bool first, cudaStream_t st) {
     float *s0 = ws.P[0], *s1 = ws.P[1], *spare = ws.P[2];
     // injective_pad + split (RevResNet.py:24-28, :8-12): s0 = [x, 0...], s1 = 0
-    if (launch_image_to_state(x, s0, n->cfg.in_channel, n->c0, H, W, st)) return 1;
+    if (launch_image_to_state(x, s0, n->cfg.in_channel, n->c0, H, W, first ? ws.status : nullptr, st)) return 1;
     VST_CUDA_OK(cudaMemsetAsync(s1, 0, p4_floats(n->c0, H, W) * sizeof(float), st));
     count_launch(1);
 
@@ -259,10 +264,10 @@ static int forward_one(const vst_revnet* n, const float* packed, const float* x,
 }
 
 static int inverse_one(const vst_revnet* n, const float* packed, const float* z, float* x, int H, int W,
-                       const Workspace& ws, cudaStream_t st) {
+                       const Workspace& ws, bool first, cudaStream_t st) {
     float *s0 = ws.P[0], *s1 = ws.P[1], *spare = ws.P[2];
     int h = H / n->down, w = W / n->down;
-    if (launch_latent_gather(z, s0, s1, n->cr_channel, h, w, n->cfg.sp_steps, st)) return 1;
+    if (launch_latent_gather(z, s0, s1, n->cr_channel, h, w, n->cfg.sp_steps, first ? ws.status : nullptr, st)) return 1;
     for (int i = (int)n->cr.size() - 1; i >= 0; --i) {
         if (run_F(n, n->cr[i], packed, s0, h, w, ws, s1, s1, EPI_SUB, st)) return 1;
         std::swap(s0, s1);
@@ -388,7 +393,7 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
 extern "C" size_t vst_revnet_workspace_bytes(const vst_revnet* net, int B, int H, int W) {
     (void)B;
     if (!net || H <= 0 || W <= 0) return 0;
-    return (3 * half_state_floats(net, H, W) + 2 * temp_floats(net, H, W)) * sizeof(float);
+    return (WS_HEADER_FLOATS + 3 * half_state_floats(net, H, W) + 2 * temp_floats(net, H, W)) * sizeof(float);
 }
 
 static int check_hw(const vst_revnet* net, int B, int H, int W) {
@@ -409,7 +414,7 @@ extern "C" int vst_revnet_forward(const vst_revnet* net, const void* packed, con
     const size_t xs = (size_t)net->cfg.in_channel * H * W;
     const size_t zs = (size_t)2 * net->cr_channel * (H / net->down) * (W / net->down);
     for (int b = 0; b < B; ++b)
-        if (forward_one(net, (const float*)packed, x + b * xs, z + b * zs, H, W, ws, (cudaStream_t)stream)) return 1;
+        if (forward_one(net, (const float*)packed, x + b * xs, z + b * zs, H, W, ws, b == 0, (cudaStream_t)stream)) return 1;
     return 0;
 }
 
@@ -422,6 +427,6 @@ extern "C" int vst_revnet_inverse(const vst_revnet* net, const void* packed, con
     const size_t xs = (size_t)net->cfg.in_channel * H * W;
     const size_t zs = (size_t)2 * net->cr_channel * (H / net->down) * (W / net->down);
     for (int b = 0; b < B; ++b)
-        if (inverse_one(net, (const float*)packed, z + b * zs, x + b * xs, H, W, ws, (cudaStream_t)stream)) return 1;
+        if (inverse_one(net, (const float*)packed, z + b * zs, x + b * xs, H, W, ws, b == 0, (cudaStream_t)stream)) return 1;
     return 0;
 }

@@ -226,6 +226,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
+// fp16 operand range guard (precision f16x2): every fp32 -> fp16 "hi" conversion folds |hi| into a per-thread running
+// maximum (one HMNMX2 per two values); a thread whose maximum reached inf raises VST_STATUS_F16_RANGE in the call's
+// status word when its role ends.  Overflow is otherwise silent: hi = inf makes lo = -inf, the products NaN, and a
+// ReLU turns NaN into 0.
+__device__ __forceinline__ uint32_t range_fold(uint32_t hmax, uint32_t hi_pair) {
+    uint32_t r;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(hmax), "r"(hi_pair & 0x7fff7fffu));
+    return r;
+}
+__device__ __forceinline__ void range_report(uint32_t hmax, int* status) {
+    if (status && (((hmax & 0x7c00u) == 0x7c00u) || ((hmax & 0x7c000000u) == 0x7c000000u))) atomicOr(status, VST_STATUS_F16_RANGE);
+}
+
 __device__ __forceinline__ float tf32_round(float x) {   // round-to-nearest onto the tf32 grid
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }

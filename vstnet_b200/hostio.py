@@ -17,17 +17,25 @@ SEG_COLORS = np.array([  # ref: utils/utils.py:106-116, index = label
     (0, 255, 255), (255, 0, 255)], dtype=np.int32)
 
 
-def img_resize(img, max_size, down_scale=None):
-    """Cap the long edge at ``max_size`` and floor H, W to multiples of ``down_scale`` (PIL bicubic)."""
-    w, h = img.size
-    if max(w, h) > max_size:
-        w = int(1.0 * img.size[0] / max(img.size) * max_size)
-        h = int(1.0 * img.size[1] / max(img.size) * max_size)
-        img = img.resize((w, h), Image.BICUBIC)
+def resized_dims(w, h, max_size, down_scale=None):
+    """The (w, h) sequence ``img_resize`` goes through: first the long edge capped at ``max_size`` (aspect kept,
+    both sides truncated toward zero), then both sides floored to multiples of ``down_scale``.  Each entry is one
+    PIL bicubic resize in the reference (utils/utils.py:90-101) — including the second one when it is a no-op."""
+    steps = []
+    long_edge = max(w, h)
+    if long_edge > max_size:
+        w, h = int(1.0 * w / long_edge * max_size), int(1.0 * h / long_edge * max_size)
+        steps.append((w, h))
     if down_scale is not None:
-        w = w // down_scale * down_scale
-        h = h // down_scale * down_scale
-        img = img.resize((w, h), Image.BICUBIC)
+        w, h = w // down_scale * down_scale, h // down_scale * down_scale
+        steps.append((w, h))
+    return steps
+
+
+def img_resize(img, max_size, down_scale=None):
+    """Cap the long edge at ``max_size`` and floor H, W to multiples of ``down_scale`` (PIL bicubic per step)."""
+    for size in resized_dims(img.size[0], img.size[1], max_size, None if down_scale is None else int(down_scale)):
+        img = img.resize(size, Image.BICUBIC)
     return img
 
 

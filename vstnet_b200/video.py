@@ -19,23 +19,110 @@ def shard_frames(n_frames, rank, world_size):
     return list(range(rank, n_frames, world_size))
 
 
-def broadcast_style_stats(pre, nbytes_of, device, group=None, src=0):
-    """The path's only collective: ``src`` sends the hoisted style statistics (an opaque byte buffer per
-    sample, 8.6 KB for C=32 / one label) to every rank.  ``pre`` is the dict of
-    ``cWCT.precompute_style`` on ``src`` and ``None`` elsewhere; ``nbytes_of(C, L)`` sizes one buffer.
-    Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+STYLE_HEADER_BYTES = 32          # 4 x int64: L, masked, C, B
+
+
+def pack_style_stats(pre):
+    """``precompute_style`` dict -> ONE uint8 device buffer: [L, masked, C, B as int64 | stats of sample 0 | ...]."""
+    head = torch.tensor([pre["L"], int(pre["masked"]), pre["C"], len(pre["stats"])], dtype=torch.int64)
+    dev = pre["stats"][0].device
+    return torch.cat([head.view(torch.uint8).to(dev)] + [s.reshape(-1) for s in pre["stats"]])
+
+
+def unpack_style_stats(buf):
+    head = buf[:STYLE_HEADER_BYTES].cpu().view(torch.int64).tolist()
+    L, masked, C_, B = (int(v) for v in head)
+    per = (buf.numel() - STYLE_HEADER_BYTES) // max(B, 1)
+    stats = [buf[STYLE_HEADER_BYTES + i * per:STYLE_HEADER_BYTES + (i + 1) * per] for i in range(B)]
+    return {"stats": stats, "L": L, "masked": bool(masked), "C": C_}
+
+
+def broadcast_style_stats(pre, nbytes, device, group=None, src=0):
+    """The path's only collective, exactly ONE ``broadcast``: ``src`` sends the hoisted style statistics
+    (header + one opaque stats block per sample; 8.6 KB for C = 32 / one label) to every rank.  ``pre`` is the
+    dict of ``cWCT.precompute_style`` on ``src`` and ``None`` elsewhere; ``nbytes`` is the buffer size, which every
+    rank can compute without communication when the style layout is known up front (``style_buffer_bytes``), as it
+    is for the unmasked video path.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
     import torch.distributed as dist
     rank = dist.get_rank(group)
-    meta = torch.zeros(4, dtype=torch.int64, device=device)
-    if rank == src:
-        meta[:] = torch.tensor([pre["L"], int(pre["masked"]), pre["C"], len(pre["stats"])])
-    dist.broadcast(meta, src=src, group=group)
-    L, masked, C_, B = (int(v) for v in meta.tolist())
-    nbytes = nbytes_of(C_, L)
-    stats = pre["stats"] if rank == src else [torch.empty(nbytes, dtype=torch.uint8, device=device) for _ in range(B)]
-    for s in stats:
-        dist.broadcast(s, src=src, group=group)
-    return {"stats": stats, "L": L, "masked": bool(masked), "C": C_}
+    buf = pack_style_stats(pre) if rank == src else torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if buf.numel() != nbytes:
+        raise ValueError("style statistics occupy %d bytes, the ranks agreed on %d" % (buf.numel(), nbytes))
+    dist.broadcast(buf, src=src, group=group)
+    return unpack_style_stats(buf)
+
+
+def style_buffer_bytes(nbytes_of, C_, L=1, B=1):
+    """Size of the broadcast buffer for B samples of a C-channel latent with L label slots."""
+    return STYLE_HEADER_BYTES + B * int(nbytes_of(C_, L))
+
+
+class SharedFrameRing:
+    """Ordered delivery of stylized uint8 frames from the ranks of ONE node to a single consumer (the video writer on
+    rank 0) through a bounded ring in shared host memory — a file-backed mapping under ``/dev/shm`` — instead of
+    pickling every frame through ``dist.gather_object`` (at 700 frames/s x 6.2 MB that host path, not the GPUs,
+    would bound an 8-GPU run).  No device collective and no serialisation: a producer copies its frame into slot
+    ``i % slots`` and publishes ``ready[slot] = i + 1``; the consumer takes frames 0, 1, 2, ... and publishes
+    ``consumed``; a producer waits while ``i - slots >= consumed``.  x86 keeps the frame bytes ahead of the flag."""
+
+    HEADER = 4096          # int64 words: [0] consumed, [8 + slot] ready
+
+    def __init__(self, path, frame_shape, slots, create):
+        import numpy as np
+        self.path, self.slots = path, int(slots)
+        self.frame_shape = tuple(int(v) for v in frame_shape)
+        self.frame_bytes = int(np.prod(self.frame_shape))
+        if 8 + self.slots > self.HEADER // 8:
+            raise ValueError("at most %d slots" % (self.HEADER // 8 - 8))
+        total = self.HEADER + self.slots * self.frame_bytes
+        if create:
+            with open(path, "wb") as f:
+                f.truncate(total)
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(total,))
+        self._flags = self._mm[:self.HEADER].view(np.int64)
+        self._frames = self._mm[self.HEADER:].reshape((self.slots,) + self.frame_shape)
+
+    @staticmethod
+    def default_path(tag):
+        import os
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+        return os.path.join(base, "vstb200_frames_%s" % tag)
+
+    def put(self, i, frame, timeout=600.0):
+        import time
+        t0 = time.monotonic()
+        while i - self.slots >= int(self._flags[0]):
+            if time.monotonic() - t0 > timeout:
+                raise TimeoutError("frame %d: the consumer has not freed slot %d" % (i, i % self.slots))
+            time.sleep(0.0002)
+        k = i % self.slots
+        self._frames[k][...] = frame.numpy() if hasattr(frame, "numpy") else frame
+        self._flags[8 + k] = i + 1
+
+    def get(self, i, timeout=600.0):
+        """Frame i (a view into the ring, valid until ``release(i)``)."""
+        import time
+        t0 = time.monotonic()
+        k = i % self.slots
+        while int(self._flags[8 + k]) != i + 1:
+            if time.monotonic() - t0 > timeout:
+                raise TimeoutError("frame %d was never delivered" % i)
+            time.sleep(0.0002)
+        return self._frames[k]
+
+    def release(self, i):
+        self._flags[0] = i + 1
+
+    def close(self, unlink=False):
+        import os
+        self._frames = self._flags = None
+        mm, self._mm = self._mm, None
+        del mm
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
 
 
 class VideoStylizer:
@@ -53,20 +140,26 @@ class VideoStylizer:
 
     # ------------------------------------------------------------------ style (once per video)
     @torch.no_grad()
-    def set_style(self, style=None, style_seg=None, group=None, src=0):
-        """Encode the style image and hoist its statistics; broadcast from ``src`` if a process
-        group is initialised.  Non-source ranks may pass ``style=None`` but must know its shape
-        through the broadcast metadata."""
+    def set_style(self, style=None, style_seg=None, group=None, src=0, masked=False):
+        """Encode the style image and hoist its statistics; ONE broadcast from ``src`` if a process group is
+        initialised.  Non-source ranks pass ``style=None`` (and ``masked=True`` if ``src`` has a ``style_seg``)."""
         import torch.distributed as dist
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         rank = dist.get_rank(group) if distributed else 0
         dev = next(self.net.parameters()).device
+        with torch.cuda.device(dev):
+            self.net._packed_weights(dev)          # every rank packs here, on the caller's stream, before any compute
+                                                   # stream is forked (non-source ranks never run the net in set_style)
+        # multi-GPU: the ranks agree on the buffer size without communication — C from the network, L = 1 unmasked,
+        # L = 256 (every uint8 label has a slot) masked
+        masked = bool(masked or style_seg is not None)
+        L = None if not distributed else (_lib.MAX_LABELS if masked else 1)
         if not distributed or rank == src:
             zs = self.net(style.to(dev), forward=True)
-            pre = self.cwct.precompute_style(zs, style_seg)
+            pre = self.cwct.precompute_style(zs, style_seg, n_labels=L if masked else None)
         if distributed:
-            nbytes_of = lambda C_, L: int(self._lib.vst_cwct_stats_bytes(C_, L))
-            pre = broadcast_style_stats(pre if rank == src else None, nbytes_of, dev, group, src)
+            nbytes = style_buffer_bytes(self._lib.vst_cwct_stats_bytes, self.net.latent_channels, L, 1)
+            pre = broadcast_style_stats(pre if rank == src else None, nbytes, dev, group, src)
         self.style_pre = pre
         return pre
 
@@ -89,13 +182,13 @@ class VideoStylizer:
         cur = torch.cuda.current_stream(dev)
         cs = self._compute_streams(dev)
         n = len(cs)
-        start = torch.cuda.Event()
-        start.record(cur)
         inflight = []                                   # (output, done event) in frame order
         for i, f in enumerate(frames):
             s = cs[i % n]
-            if i < n:
-                s.wait_event(start)                     # inputs produced on the caller's stream are complete
+            ev_in = torch.cuda.Event()                  # the frame may be produced lazily on the caller's stream (a
+            ev_in.record(cur)                           # generator running device work): order it, and everything
+            s.wait_event(ev_in)                         # enqueued before, ahead of its compute stream
+            f.record_stream(s)
             with torch.cuda.stream(s):
                 y = self.stylize(f, None if content_segs is None else content_segs[i])
                 ev = torch.cuda.Event()
@@ -154,31 +247,40 @@ class VideoStylizer:
         """Pipelined end-to-end path for a sequence of HOST uint8 ``[H,W,3]`` frames (what cv2 / PIL deliver;
         pinned memory makes the copies asynchronous).  Yields pinned uint8 ``[H,W,3]`` host tensors in order,
         ``n_streams`` frames behind the input: frame i is stylized on compute stream ``i % n_streams`` while later
-        frames are uploaded and earlier ones downloaded on two copy streams (a ring of ``n_streams + 1`` device /
-        host staging slots).  Each yielded tensor stays valid until ``n_streams`` more frames have been yielded."""
+        frames are uploaded and earlier ones downloaded on two copy streams (a ring of ``n_streams + 1`` device
+        staging slots and ``2 n_streams + 2`` host slots).  A yielded tensor is a view of a ring slot: it stays valid
+        until ``n_streams`` more frames have been yielded (the host ring is deep enough that no download in flight
+        targets a slot the consumer may still hold) — copy it if it must live longer."""
         dev = next(self.net.parameters()).device
         cs = self._compute_streams(dev)
         n = len(cs)
-        R = n + 1                                                      # staging ring depth
+        R = n + 1                                                      # device staging ring depth
+        RH = 2 * R                                                     # host ring: frame j's slot is re-targeted by the
+                                                                       # download of frame j + RH, enqueued only after
+                                                                       # frame j + RH - n - 1 >= j + n + 1 was yielded
         s_in, s_out = self._streams(dev)
         st = self._pin.get(("stream", str(dev)))
         if st is None or len(st["din"]) != R:
-            st = {"din": [None] * R, "dout": [None] * R, "hout": [None] * R,
-                  "ev": [[torch.cuda.Event() for _ in range(R)] for _ in range(3)]}
+            st = {"din": [None] * R, "dout": [None] * R, "hout": [None] * RH,
+                  "ev": [[torch.cuda.Event() for _ in range(R)] for _ in range(2)],
+                  "ev_out": [torch.cuda.Event() for _ in range(RH)]}
             self._pin[("stream", str(dev))] = st                       # staging survives across calls (pinning is slow)
         din, dout, hout = st["din"], st["dout"], st["hout"]
-        ev_in, ev_done, ev_out = st["ev"]
+        ev_in, ev_done = st["ev"]
+        ev_out = st["ev_out"]
         start = torch.cuda.Event()
         start.record(torch.cuda.current_stream(dev))
         pending = []
         for i, f in enumerate(frames):
             b = i % R
+            hb = i % RH
             c = cs[i % n]
             H, W = int(f.shape[0]), int(f.shape[1])
             if din[b] is None or din[b].shape != f.shape:
                 din[b] = torch.empty(H, W, 3, dtype=torch.uint8, device=dev)
                 dout[b] = torch.empty(H, W, 3, dtype=torch.uint8, device=dev)
-                hout[b] = torch.empty(H, W, 3, dtype=torch.uint8).pin_memory()
+            if hout[hb] is None or hout[hb].shape != f.shape:
+                hout[hb] = torch.empty(H, W, 3, dtype=torch.uint8).pin_memory()
             with torch.cuda.stream(s_in):
                 if i >= R:
                     s_in.wait_event(ev_done[b])            # frame i-R no longer reads this input buffer
@@ -188,7 +290,7 @@ class VideoStylizer:
                 c.wait_event(start)
             c.wait_event(ev_in[b])
             if i >= R:
-                c.wait_event(ev_out[b])                    # frame i-R's download has left dout[b]
+                c.wait_event(ev_out[(i - R) % RH])         # frame i-R's download has left dout[b]
             with torch.cuda.stream(c):
                 x = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
                 _lib.check(self._lib.vst_frame_u8_to_f32(din[b].data_ptr(), x.data_ptr(), H, W, int(bgr), c.cuda_stream),
@@ -199,9 +301,9 @@ class VideoStylizer:
                 ev_done[b].record(c)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[b])
-                hout[b].copy_(dout[b], non_blocking=True)
-                ev_out[b].record(s_out)
-            pending.append(b)
+                hout[hb].copy_(dout[b], non_blocking=True)
+                ev_out[hb].record(s_out)
+            pending.append(hb)
             if len(pending) > n:
                 p = pending.pop(0)
                 ev_out[p].synchronize()
