@@ -7,10 +7,15 @@ hoisted once (rank 0) and NCCL-broadcast; every rank then stylizes its own frame
 one 1920x1080 frame per rank: encode -> cWCT stats/factor/apply -> decode.  `value` is whole-job
 frames/s with frames resident in HBM; `e2e` is the same through `VideoStylizer.stylize_stream`
 with HOST buffers (pinned uint8 HWC frame H2D + uint8 result D2H inside the timed region, pipelined).
-`images` (N = 1 only) adds ms per image for the other BASELINE configs (cfg1/2/3/5).
+Extras: `images` (N = 1) — ms per image of the other BASELINE configs (cfg1/2/3/5) with the CPU oracle
+timed beside them (cfg1/2/3) and the parity figures of the same run; `sustained` — 240 frames back to
+back; `strong` — the whole 240-frame job (style encode + broadcast + frames + ordered delivery).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nproc-per-node N ... bench.py --gpus N ...
+
+`--impl reference` times the reference's CPU implementation of the same path (oracle/vst_oracle.py, the
+torch CPU ops the reference issues) and imports nothing of the product.
 """
 import argparse
 import json
@@ -29,6 +34,8 @@ FRAMES_PER_VIDEO = 240
 CONV_FLOP_PER_PX = 609984.0      # 96 convs per pass, 2*MAC
 METRIC = "1080p video frames/s"
 UNIT = "frames/s"
+WORKLOAD = "cfg4 photorealistic video 1920x1080, style hoisted + broadcast, random-init RevResNet"
+MODES = {"photo": dict(hidden_dim=16, sp_steps=2), "art": dict(hidden_dim=64, sp_steps=1)}
 
 
 def peaks():
@@ -61,6 +68,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -93,17 +101,74 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
+# synthetic inputs of the BASELINE configs (shared with tests/test_baseline_configs.py)
+# ----------------------------------------------------------------------------------------------
+def blocky_mask(h, w, gy, gx, perm):
+    import numpy as np
+    m = np.zeros((h, w), np.uint8)
+    ys, xs = np.linspace(0, h, gy + 1).astype(int), np.linspace(0, w, gx + 1).astype(int)
+    for i in range(gy):
+        for j in range(gx):
+            m[ys[i]:ys[i + 1], xs[j]:xs[j + 1]] = perm[i * gx + j]
+    return m[None]
+
+
+IMAGE_CONFIGS = {
+    # name: (mode, H = W, alpha_c, masked)
+    "cfg1_photo_512": ("photo", 512, None, False),
+    "cfg2_art_1024_alpha0.5": ("art", 1024, 0.5, False),
+    "cfg3_photo_1024_masked8": ("photo", 1024, None, True),
+    "cfg5_art_4096": ("art", 4096, None, False),
+}
+
+
+def image_config_inputs(name, size=None):
+    """CPU tensors of one BASELINE image config: (mode, content, style, alpha_c, cmask, smask).  SURVEY.md 8(d):
+    torch.rand images (seed 7), 8 blocky labels (2x4 content grid, permuted 4x2 style grid)."""
+    import torch
+    mode, s0, alpha, masked = IMAGE_CONFIGS[name]
+    s = int(size or s0)
+    g = torch.Generator().manual_seed(7)
+    c = torch.rand(1, 3, s, s, generator=g)
+    st = torch.rand(1, 3, s, s, generator=g)
+    cm = blocky_mask(s, s, 2, 4, [0, 1, 2, 3, 4, 5, 6, 7]) if masked else None
+    sm = blocky_mask(s, s, 4, 2, [3, 1, 0, 2, 7, 6, 4, 5]) if masked else None
+    return mode, c, st, alpha, cm, sm
+
+
+def oracle_stylize(sd, mode, c, s, alpha, cm, sm, with_roundtrip=False):
+    """The CPU oracle on one image config -> (stylized, seconds, reference round-trip error stats or None)."""
+    import torch
+    from oracle import vst_oracle as O
+    kw = MODES[mode]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        zc, zs = O.revnet_forward(sd, c, **kw), O.revnet_forward(sd, s, **kw)
+        if cm is not None:
+            zcs = O.cwct_transfer_seg(zc, zs, cm, sm)
+        elif alpha is not None:
+            zcs = O.cwct_interpolation(zc, [zs], [1.0], alpha)
+        else:
+            zcs = O.cwct_transfer(zc, zs)
+        y = O.revnet_inverse(sd, zcs, **kw)
+        float(y[0, 0, 0, 0])
+        dt = time.perf_counter() - t0
+        rt = None
+        if with_roundtrip:
+            e = (O.revnet_inverse(sd, zc, **kw) - c).abs()
+            rt = (float(e.max()), float(e.mean()))
+    return y, dt, rt
+
+
+# ----------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (a torch-fp32 port of the reference path) on the host cores
 # ----------------------------------------------------------------------------------------------
 def cpu_frames_per_s(h, w, steps, warmup, threads):
     """Time `steps` hoisted-style frames of h x w on the CPU oracle; returns (frames/s at h x w, seconds/frame)."""
     import torch
     from oracle import vst_oracle as O
-    from vstnet_b200 import RevResNet
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    net = RevResNet(hidden_dim=16, sp_steps=2)
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = O.init_state_dict(0, **MODES["photo"])           # the reference's default init; nothing of the product
     g = torch.Generator().manual_seed(99)
     style = torch.rand(1, 3, h, w, generator=g)
     frames = [torch.rand(1, 3, h, w, generator=g) for _ in range(2)]
@@ -144,52 +209,41 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     value, sample, h, w = bounded_cpu_sample(150.0, args.steps, args.warmup, threads)
+    assert "vstnet_b200" not in sys.modules, "the reference arm must not load the product"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg4 photorealistic video 1920x1080, style hoisted, random-init RevResNet",
-                   "frames_per_video": FRAMES_PER_VIDEO},
+        "config": {"workload": WORKLOAD, "frames_per_video": FRAMES_PER_VIDEO},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is Python and cannot travel to the GPU box; this is oracle/vst_oracle.py, the same "
-                "torch CPU ops (F.conv2d, linalg.cholesky) the reference issues, on all host cores",
+                "torch CPU ops (F.conv2d, linalg.cholesky) the reference issues, on all host cores, weights from "
+                "oracle.init_state_dict (the reference's default init); no module of the product is imported",
     }
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
-# the other BASELINE configs (single images): reported as extras, "ms per image" = 2 encodes + cWCT + decode
+# the other BASELINE configs (single images): extras — "ms per image" = 2 encodes + cWCT + decode on the GPU,
+# the CPU oracle timed on the same inputs (cfg1/2/3), and the parity of the two results
 # ----------------------------------------------------------------------------------------------
 def image_configs_ms(dev, precision, with_cpu):
-    import numpy as np
     import torch
     from vstnet_b200 import RevResNet, cWCT
 
-    def blocky(h, w, gy, gx, perm):
-        m = np.zeros((h, w), np.uint8)
-        ys, xs = np.linspace(0, h, gy + 1).astype(int), np.linspace(0, w, gx + 1).astype(int)
-        for i in range(gy):
-            for j in range(gx):
-                m[ys[i]:ys[i + 1], xs[j]:xs[j + 1]] = perm[i * gx + j]
-        return m[None]
-
     out = {}
     nets = {}
-    for name, mode, size, alpha, masked in (("cfg1_photo_512", "photo", 512, None, False),
-                                            ("cfg2_art_1024_alpha0.5", "art", 1024, 0.5, False),
-                                            ("cfg3_photo_1024_masked8", "photo", 1024, None, True),
-                                            ("cfg5_art_4096", "art", 4096, None, False)):
+    threads = os.cpu_count() or 1
+    for name, (mode, size, alpha, masked) in IMAGE_CONFIGS.items():
         if mode not in nets:
             torch.manual_seed(0)
-            kw = dict(hidden_dim=16, sp_steps=2) if mode == "photo" else dict(hidden_dim=64, sp_steps=1)
-            nets[mode] = RevResNet(**kw, precision=precision).to(dev).eval()
+            nets[mode] = RevResNet(**MODES[mode], precision=precision).to(dev).eval()
         net, cw = nets[mode], cWCT()
-        g = torch.Generator(device=dev).manual_seed(7)
-        c = torch.rand(1, 3, size, size, device=dev, generator=g)
-        s = torch.rand(1, 3, size, size, device=dev, generator=g)
-        cm = torch.from_numpy(blocky(size, size, 2, 4, [0, 1, 2, 3, 4, 5, 6, 7])).to(dev) if masked else None
-        sm = torch.from_numpy(blocky(size, size, 4, 2, [3, 1, 0, 2, 7, 6, 4, 5])).to(dev) if masked else None
+        _, c_h, s_h, _, cm_h, sm_h = image_config_inputs(name)
+        c, s = c_h.to(dev), s_h.to(dev)
+        cm = torch.from_numpy(cm_h).to(dev) if masked else None
+        sm = torch.from_numpy(sm_h).to(dev) if masked else None
 
         def run():
             zc, zs = net.encode_pair(c, s)               # what image_transfer.py's stylize() does
@@ -208,31 +262,76 @@ def image_configs_ms(dev, precision, with_cpu):
         reps = 3
         a.record()
         for _ in range(reps):
-            run()
+            y = run()
         b.record()
         torch.cuda.synchronize()
         out[name] = {"gpu_ms": round(a.elapsed_time(b) / reps, 3)}
-        del c, s
+        if with_cpu and size <= 1024:
+            # CPU oracle on the same inputs and weights: the metric's "vs host-CPU torch" half, and the parity
+            # of this very run (stylized pixels; round trip against the reference's own on the same input)
+            torch.set_num_threads(threads)
+            sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+            y_ref, dt, rt = oracle_stylize(sd, mode, c_h, s_h, alpha, cm_h, sm_h, with_roundtrip=True)
+            e = (net.inverse(net(c)) - c).abs()
+            out[name].update({
+                "cpu_ms": round(dt * 1e3, 1), "cpu_cores": threads,
+                "max_abs_vs_oracle": float((y.cpu() - y_ref).abs().max()),
+                "roundtrip_max": float(e.max()), "roundtrip_mean": float(e.mean()),
+                "roundtrip_ratio_vs_reference": {"max": float(e.max()) / max(rt[0], 1e-30),
+                                                 "mean": float(e.mean()) / max(rt[1], 1e-30)}})
+        del c, s, y
         torch.cuda.empty_cache()
-    if with_cpu:                      # the reference's own CPU-runnable case (configs[0]) on the host cores
-        from oracle import vst_oracle as O
-        torch.manual_seed(0)
-        net = RevResNet(hidden_dim=16, sp_steps=2)
-        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-        gc = torch.Generator().manual_seed(7)
-        c, s = torch.rand(1, 3, 512, 512, generator=gc), torch.rand(1, 3, 512, 512, generator=gc)
-        with torch.no_grad():
-            t0 = time.perf_counter()
-            y = O.revnet_inverse(sd, O.cwct_transfer(O.revnet_forward(sd, c), O.revnet_forward(sd, s)))
-            float(y[0, 0, 0, 0])
-            out["cfg1_photo_512"]["cpu_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
-            out["cfg1_photo_512"]["cpu_cores"] = os.cpu_count()
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# strong scaling: the WHOLE job — one 240-frame video over all ranks, host buffers, ordered delivery
+# ----------------------------------------------------------------------------------------------
+def strong_scaling_job(vs, style, host_pool, rank, world, dev, barrier):
+    """Times set_style (style encode + statistics on rank 0 + the single broadcast) + every rank's share of
+    FRAMES_PER_VIDEO frames through stylize_stream (H2D / D2H inside) + delivery of all frames IN ORDER to rank 0's
+    consumer through the shared-memory frame ring (what video_transfer.py's writer reads).  Wall clock between two
+    barriers, on rank 0."""
+    import torch
+    from vstnet_b200.video import SharedFrameRing, shard_frames
+    mine = shard_frames(FRAMES_PER_VIDEO, rank, world)
+    path = SharedFrameRing.default_path("bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid()))
+    slots = 4 * world * vs.n_streams
+    barrier()
+    t0 = time.perf_counter()
+    vs.set_style(style)
+    if rank == 0:
+        ring = SharedFrameRing(path, (H, W, 3), slots, create=True)
+    barrier()
+    if rank != 0:
+        ring = SharedFrameRing(path, (H, W, 3), slots, create=False)
+    consumer, seen = None, []
+    if rank == 0:
+        def consume():
+            for i in range(FRAMES_PER_VIDEO):
+                seen.append(int(ring.get(i)[0, 0, 0]))
+                ring.release(i)
+        consumer = threading.Thread(target=consume)
+        consumer.start()
+    for i, o in zip(mine, vs.stylize_stream(host_pool[i % len(host_pool)] for i in mine)):
+        ring.put(i, o)
+    if consumer is not None:
+        consumer.join()
+    barrier()
+    dt = time.perf_counter() - t0
+    ring.close(unlink=(rank == 0))
+    return {"frames": FRAMES_PER_VIDEO, "seconds": dt, "value": FRAMES_PER_VIDEO / dt, "unit": UNIT,
+            "delivered_in_order": len(seen) if rank == 0 else None,
+            "includes": "style encode + stats (rank 0), one NCCL broadcast, H2D/D2H of every frame, ordered delivery "
+                        "to rank 0 through the shared-memory frame ring; wall clock between barriers"}
 
 
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+F16_KERNELS = ("rev_block_tc", "conv3x3_tch", "conv3x3_tcH")      # kernel classes that issue kind::f16 UMMAs in f16x2 mode
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -249,7 +348,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     K = args.steps if args.steps is not None else max(1, FRAMES_PER_VIDEO // world // 4)
-    Wm = args.warmup if args.warmup is not None else 3
+    Wm = max(3, args.warmup if args.warmup is not None else 4)
 
     torch.manual_seed(0)
     net = RevResNet(hidden_dim=16, sp_steps=2, precision=args.precision).to(dev).eval()
@@ -258,7 +357,7 @@ def run_ours(args):
     style = None
     if rank == 0:
         style = torch.rand(1, 3, H, W, device=dev, generator=gen.manual_seed(4321))
-    vs.set_style(style)                               # rank 0 encodes + factorises, one broadcast
+    vs.set_style(style)                               # rank 0 encodes + factorises, ONE broadcast
     pool = 4                                          # distinct resident frames cycled through
     frames = [torch.rand(1, 3, H, W, device=dev, generator=gen.manual_seed(1234 + rank * pool + i)) for i in range(pool)]
 
@@ -267,26 +366,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`)
-    Wm = max(Wm, 4 * vs.n_streams)                    # every compute stream's workspace / allocator pool is warm
-    for _ in vs.stylize_frames(frames[i % pool] for i in range(Wm)):
-        pass
+    def timed_frames(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in vs.stylize_frames(frames[i % pool] for i in range(n)):      # frames dealt to vs.n_streams compute streams
+            pass
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- device-resident throughput (`value`).  Setup (not warm-up): one frame per compute stream allocates that
+    # stream's workspace and allocator pool; then exactly W warm-up steps, then exactly K timed steps.
+    timed_frames(vs.n_streams)
+    timed_frames(Wm)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local).start() if rank == 0 else None
     n0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for y in vs.stylize_frames(frames[i % pool] for i in range(K)):      # frames dealt to vs.n_streams compute streams
-        pass
-    e1.record()
-    torch.cuda.synchronize()
+    ms_local = timed_frames(K)
     launches = _lib.launch_count() - n0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     # ---- per-kernel durations: the SAME K steps once more with a CUDA-event pair around every launch
-    # (the library's profiler), kept out of the `value` pass because ~330 event pairs per frame perturb it
+    # (the library's profiler), single stream, kept out of the `value` pass because ~330 event pairs per frame perturb it
     _lib.profile_enable(True)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
@@ -298,17 +399,31 @@ def run_ours(args):
     prof = _lib.profile_collect()
     ms_prof = p0.elapsed_time(p1)
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    ms = torch.tensor([ms_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     value = world * K / (ms / 1e3)
 
+    # ---- sustained: a whole video's worth of frames back to back (power-cap behaviour on the record)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(K, FRAMES_PER_VIDEO // world)
+        barrier()
+        s2 = ClockSampler(local).start() if rank == 0 else None
+        ms_s = torch.tensor([timed_frames(n_sus)], device=dev, dtype=torch.float64)
+        barrier()
+        ck = s2.stop() if rank == 0 else None
+        if world > 1:
+            dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+        sustained = {"frames": world * n_sus, "value": world * n_sus / (float(ms_s.item()) / 1e3), "unit": UNIT,
+                     "ms_per_step": float(ms_s.item()) / n_sus, "clocks": ck}
+
     # ---- end to end through the host-buffer API (`e2e`): pinned uint8 HWC frames in (what a video decoder
     # delivers), pinned uint8 HWC frames out, both copies inside the timed region, pipelined by
     # VideoStylizer.stylize_stream (upload of frame i+1 and download of frame i-1 overlap frame i)
     host_frames = [(f[0].permute(1, 2, 0) * 255).round().clamp(0, 255).byte().contiguous().cpu().pin_memory() for f in frames]
-    for _ in vs.stylize_stream(host_frames[i % pool] for i in range(max(Wm, 2 * vs.n_streams))):
+    for _ in vs.stylize_stream(host_frames[i % pool] for i in range(max(Wm, 2 * vs.n_streams + 2))):
         pass
     barrier()
     Ke = K
@@ -331,45 +446,62 @@ def run_ours(args):
     h2d = host_frames[0].numel()
     d2h = out_host.numel()
 
+    # ---- strong scaling: the whole 240-frame job
+    strong = None
+    if not args.no_strong:
+        strong = strong_scaling_job(vs, style, host_frames, rank, world, dev, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel, from the live per-launch events of the timed region
+    # ---- per-kernel table and the roofline of the dominant kernel, from the live per-launch events
     pk = peaks()
-    kernels = []
-    for name, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
-        per = d["ms"] / max(1, d["launches"])
-        kernels.append({"kernel": name, "ms_total": round(d["ms"], 3), "launches": d["launches"],
-                        "share": round(d["ms"] / ms_prof, 4),
-                        "tflops": round(d["flops"] / d["ms"] / 1e9, 2) if d["ms"] > 0 else None,
-                        "gbs": round(d["bytes"] / d["ms"] / 1e6, 1) if d["ms"] > 0 else None,
-                        "ms_per_launch": round(per, 4)})
-    top_name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    ai = top["flops"] / max(1.0, top["bytes"])
-    traffic = None
+    issue = {"tf32": 1, "tf32x2": 2, "tf32x3": 3, "f16x2": 2}.get(args.precision, 1)
+    traffic_tab = {}
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tf):
         try:
-            traffic = json.load(open(tf)).get(top_name)
+            traffic_tab = json.load(open(tf))
         except Exception:
-            traffic = None
-    # kind::tf32 runs at half the bf16 rate, so the tensor roof of these kernels is the measured bf16 figure / 2;
-    # `achieved` counts USEFUL conv flops (one term), not the 2x / 3x issued by the split-precision modes.
-    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
-    if ai > tf32_peak * 1e3 / pk["hbm_gbs"]:                            # above the TF32 ridge -> tensor bound
-        ach = top["flops"] / top["ms"] / 1e9
-        roof = {"kernel": top_name, "bound": "tensor", "achieved": ach, "peak": tf32_peak,
-                "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
-                "peak_source": pk["source"] + " bf16 dense sustained / 2 (tf32 rate); achieved = useful 1-term flops, "
-                               "%s issues %dx" % (args.precision, {"tf32": 1, "tf32x2": 2, "tf32x3": 3, "f16x2": 2}.get(args.precision, 1))}
-    else:
-        ach = top["bytes"] / top["ms"] / 1e6
-        roof = {"kernel": top_name, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"] + " copy bandwidth"}
-    roof["launches"] = top["launches"]
-    roof["ms_per_launch"] = top["ms"] / max(1, top["launches"])
+            traffic_tab = {}
+
+    def tensor_peak(name):
+        """Dense peak of the MMA kind the kernel class issues: kind::f16 = the measured bf16 figure, kind::tf32 = half."""
+        f16 = args.precision == "f16x2" and name.startswith(F16_KERNELS)
+        return (pk["bf16_tflops_sustained"] if f16 else pk["bf16_tflops_sustained"] / 2.0), ("f16" if f16 else "tf32")
+
+    def roof_of(name, d):
+        per_ms = d["ms"] / max(1, d["launches"])
+        gbs = d["bytes"] / d["ms"] / 1e6 if d["ms"] > 0 else 0.0
+        tfl = d["flops"] / d["ms"] / 1e9 if d["ms"] > 0 else 0.0
+        tpk, kind = tensor_peak(name)
+        hbm_frac, ten_frac = gbs / pk["hbm_gbs"], tfl / tpk
+        # the roofline that bounds the kernel is the one whose floor (work / peak) is the larger
+        tensor_bound = d["flops"] > 0 and (d["flops"] * issue / (tpk * 1e12)) > (d["bytes"] / (pk["hbm_gbs"] * 1e9))
+        r = {"kernel": name, "launches": d["launches"], "ms_per_launch": per_ms, "traffic": traffic_tab.get(name)}
+        if tensor_bound:
+            r.update({"bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": ten_frac,
+                      "frac_issued": ten_frac * issue,
+                      "peak_source": "%s bf16 dense sustained%s (kind::%s); achieved = useful 1-term flops, %s issues %dx"
+                                     % (pk["source"], "" if kind == "f16" else " / 2", kind, args.precision, issue)})
+        else:
+            r.update({"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac,
+                      "peak_source": pk["source"] + " copy bandwidth"})
+        return r, hbm_frac, ten_frac
+
+    kernels = []
+    for name, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        r, hf, tfr = roof_of(name, d)
+        kernels.append({"kernel": name, "ms_total": round(d["ms"], 3), "launches": d["launches"],
+                        "share": round(d["ms"] / ms_prof, 4), "ms_per_launch": round(r["ms_per_launch"], 4),
+                        "tflops_useful": round(d["flops"] / d["ms"] / 1e9, 2) if d["ms"] > 0 else None,
+                        "gbs": round(d["bytes"] / d["ms"] / 1e6, 1) if d["ms"] > 0 else None,
+                        "bound": r["bound"], "frac": round(r["frac"], 4), "hbm_frac": round(hf, 4),
+                        "tensor_frac_useful": round(tfr, 4)})
+    top_name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    roof, _, _ = roof_of(top_name, top)
 
     # ---- CPU baseline (rank 0, N == 1 only): the oracle on the host cores, bounded sample
     cpu = None
@@ -388,9 +520,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "f16x2": "f16x2+tf32x2 (fp32 accumulate)"}.get(args.precision, args.precision), "data": "synthetic",
-        "config": {"workload": "cfg4 photorealistic video 1920x1080, style hoisted + broadcast, random-init RevResNet",
+        "config": {"workload": WORKLOAD,
                    "frames_per_video": FRAMES_PER_VIDEO, "frames_per_step_per_gpu": 1, "conv_precision": args.precision,
                    "l2": "per-frame working set (~1.5 GB of states) >> 126 MB L2; %d distinct frames cycled" % pool,
+                   "setup": "%d untimed allocation frames (one per compute stream) before the %d warm-up steps" % (vs.n_streams, Wm),
                    "parallelism": "frames sharded dp%d, no data-path collective; %d frames in flight per GPU (compute streams)" % (world, vs.n_streams)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -398,9 +531,13 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "useful_conv_tflops": 2 * CONV_FLOP_PER_PX * H * W * world * K / (ms / 1e3) / 1e12,
+        "sustained": sustained,
+        "strong": strong,
+        "kernels_from": "a separate single-stream pass over the same K steps with a CUDA-event pair around every launch "
+                        "(%.3f ms per step; `value` comes from the un-instrumented %d-stream pass)" % (ms_prof / K, vs.n_streams),
         "profile_pass_ms_per_step": ms_prof / K,
         "images": images,
-        "kernels": kernels[:12],
+        "kernels": kernels[:14],
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -414,8 +551,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f16x2", help="conv arithmetic: f16x2 (default) | tf32x2 | tf32x3 | tf32 | fp32")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the CPU side of the image configs")
     ap.add_argument("--no-images", action="store_true", help="skip the single-image configs (cfg1/2/3/5 extras)")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the 240-frame sustained extra")
+    ap.add_argument("--no-strong", action="store_true", help="skip the whole-job strong-scaling extra")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps is None:

@@ -117,6 +117,31 @@ def revnet_inverse(sd, z, nBlocks=(10, 10, 10), nStrides=(1, 2, 2), nChannels=(1
     return x[:, :in_channel].contiguous()                               # injective_pad.inverse :30-31
 
 
+def init_state_dict(seed=0, nBlocks=(10, 10, 10), nStrides=(1, 2, 2), nChannels=(16, 64, 256), mult=4,
+                    hidden_dim=16, sp_steps=2, n_cr_blocks=2):
+    """The reference's random initialisation as a plain ``state_dict`` (no module of the product involved):
+    ``torch.manual_seed(seed)``, then one default-initialised ``nn.Conv2d`` per convolution in the reference's
+    construction order (per block conv.1, conv.4, conv.7; stack first, then channel_reduction), biases zeroed.
+    ref: RevResNet.py:68-94 (residual_block.__init__ / init_layers), :119-129, :166-201."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    sd = {}
+
+    def block(prefix, channel, stride):
+        in_ch = channel if stride == 1 else channel // 4
+        mid = channel // mult
+        for k, (ci, co, st) in zip((1, 4, 7), ((in_ch, mid, stride), (mid, mid, 1), (mid, channel, 1))):
+            conv = nn.Conv2d(ci, co, kernel_size=3, stride=st, padding=0, bias=True)
+            sd["%sconv.%d.weight" % (prefix, k)] = conv.weight.detach().clone()
+            sd["%sconv.%d.bias" % (prefix, k)] = torch.zeros(co)
+
+    for i, (ch, st) in enumerate(arch_blocks(nBlocks, nStrides, nChannels)):
+        block("stack.%d." % i, ch, st)
+    for i in range(n_cr_blocks):
+        block("channel_reduction.block_list.%d." % i, hidden_dim * 4 ** sp_steps, 1)
+    return sd
+
+
 # --------------------------------------------------------------------------- cWCT
 def _chol_with_jitter(cov, eps):
     """Cholesky; on failure add eps*I, then 2eps*I, ... cumulatively.  ref: cWCT.py:111-128."""

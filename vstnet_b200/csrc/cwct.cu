@@ -287,7 +287,7 @@ __device__ void build_cov(double* A, const StatsView& sv, int l, int C, double n
     const double* G = sv.gram + (size_t)l * C * C;
     const double* s = sv.sum + (size_t)l * C;
     for (int e = threadIdx.x; e < C * (C + 1) / 2; e += blockDim.x) {
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
         while (tri(i + 1, 0) <= e) ++i;
         while (tri(i, 0) > e) --i;
         int j = e - tri(i, 0);
@@ -321,7 +321,7 @@ __device__ bool cholesky_packed(double* A, int C, int* flag) {
         __syncthreads();
         const int m = C - k - 1;   // trailing size
         for (int e = threadIdx.x; e < m * (m + 1) / 2; e += blockDim.x) {
-            int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
             while (tri(a + 1, 0) <= e) ++a;
             while (tri(a, 0) > e) --a;
             int b = e - tri(a, 0);
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) cholesky_dec_kernel(const TIO* __restrict
         if (threadIdx.x == 0) { flag = 0; bad = 0; }
         const double jit = eps * (double)(k * (k + 1) / 2);
         for (int e = threadIdx.x; e < TRI; e += blockDim.x) {
-            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
             while (tri(i + 1, 0) <= e) ++i;
             while (tri(i, 0) > e) --i;
             const int j = e - tri(i, 0);
@@ -520,6 +520,18 @@ __global__ void __launch_bounds__(256) cholesky_dec_kernel(const TIO* __restrict
         out[e] = (TIO)v;
     }
     if (threadIdx.x == 0) *status = ok ? k : -1;
+}
+
+// Packed fp32 FMA (Blackwell FFMA2): (d0, d1) += (a, a) * (b0, b1), IEEE fma per half — bit-identical to two fmaf().
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "mov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -625,9 +637,10 @@ __global__ void __launch_bounds__(256) apply_kernel(const float* __restrict__ fe
                 const float xv[4] = {x4.x - m, x4.y - m, x4.z - m, x4.w - m};
                 const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-                for (int a = 0; a < 8; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(tv[a], xv[b], acc[a][b]);
+                for (int a = 0; a < 8; ++a) {       // packed FFMA2: two pixels per issue slot (a plain FFMA issues every
+                    fma2(acc[a][0], acc[a][1], tv[a], xv[0], xv[1]);   // other cycle per sub-partition)
+                    fma2(acc[a][2], acc[a][3], tv[a], xv[2], xv[3]);
+                }
             }
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
