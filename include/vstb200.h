@@ -109,6 +109,23 @@ int vst_revnet_forward(const vst_revnet* net, const void* packed, const float* x
 int vst_revnet_inverse(const vst_revnet* net, const void* packed, const float* z, float* x,
                        int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused stylization of one frame against hoisted style statistics — the video hot path
+ * (video_transfer.py:192-206 with the loop-invariant style encode of :195 hoisted):
+ *     encode -> cWCT statistics / factor / apply ON THE NETWORK'S OWN STATE -> decode
+ * The latent z is never materialised: the statistics are taken from the two half-states that channel_reduction's
+ * spread loops (RevResNet.py:140-146) would turn into z, and T (x - mu) + beta is applied to them in place
+ * (SURVEY.md 8(f) rank 1).  frame_in / frame_out are fp32 [3,H,W] in [0,1] (io_u8 == 0) or uint8 [H,W,3]
+ * (io_u8 != 0; bgr != 0: channel order B,G,R) with ToTensor's byte/255 and the mul(255).clamp(0,255).byte()
+ * truncation of video_transfer.py:188, :211-214 folded into the first and last kernel (8(f) rank 2).
+ * style_stats: a one-label block of vst_cwct_stats over the style latent.  Results equal
+ * vst_revnet_forward + vst_cwct_stats/_factor/_apply + vst_revnet_inverse up to the summation order of the
+ * statistics.  Workspace status words: [1] Cholesky retries (-1: failed, the frame passes through unstylized),
+ * [2] validity.  vst_revnet_stylize_supported: 1 if this plan / size can take the fused path. */
+int vst_revnet_stylize_supported(const vst_revnet* net, int H, int W);
+int vst_revnet_stylize(const vst_revnet* net, const void* packed, const void* frame_in, void* frame_out, int io_u8, int bgr,
+                       int H, int W, const void* style_stats, float alpha_c, float eps, int use_double,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* -------------------------------------------------------------------------------------------
  * cWCT — replaces models/cWCT.py: whitening :134-149, coloring :152-164, cholesky_dec :111-132,
  *        _transfer :24-47, _transfer_seg :49-109, compute_label_info :166-189, interpolation
@@ -174,6 +191,23 @@ int vst_mask_resize_nearest(const uint8_t* src, int Hs, int Ws, uint8_t* dst, in
                             int* scratch /* Hd + Wd ints, device */, void* stream);
 /* fp32 CHW -> uint8 HWC, mul(255).clamp(0,255).byte() truncation (video_transfer.py:211-214) */
 int vst_frame_f32_to_u8(const float* chw, uint8_t* hwc, int H, int W, int bgr, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Mask preparation on the device.
+ * ----------------------------------------------------------------------------------------- */
+/* SegReMapping (models/segmentation/SegReMapping.py:19-76) of a uint8 label map [n]:
+ *   style_seg == NULL : self_remapping  — labels covering less than min_ratio of the map move to the first label of
+ *                       their column of the relation table `mapping` (int32 [rows][n_classes], the reference's
+ *                       ade20k_semantic_rel.npy) that is present with a ratio >= min_ratio;
+ *   style_seg != NULL : cross_remapping — labels of `seg` that the style map lacks move to the first label of their
+ *                       column that the style has.
+ * `out` may alias `seg`.  scratch: vst_seg_scratch_bytes() bytes of device memory.  No host synchronisation. */
+size_t vst_seg_scratch_bytes(void);
+int vst_seg_remap(const uint8_t* seg, long long n, const uint8_t* style_seg, long long n_style, const int* mapping,
+                  int rows, int n_classes, float min_ratio, uint8_t* out, void* scratch, void* stream);
+/* colour-coded segmentation (uint8 RGB, HWC) -> labels 0..8: exact table colours, else the nearest table colour in
+ * L1 (utils/utils.py:105-137, load_segment / change_seg). */
+int vst_seg_labels_from_colors(const uint8_t* rgb_hwc, long long n, uint8_t* labels, void* stream);
 
 #ifdef __cplusplus
 }

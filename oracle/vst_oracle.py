@@ -237,3 +237,59 @@ def cwct_transfer_seg(zc, zs, cmask, smask, eps=2e-5):
             si = torch.from_numpy(np.nonzero(sm == l)[0])
             out[i][:, ci] = wct_2d(xc[:, ci], xs[:, si], eps)
     return out.reshape(zc.shape)
+
+
+# --------------------------------------------------------------------------- mask preparation
+def seg_self_remapping(seg, table, min_ratio):
+    """ref: models/segmentation/SegReMapping.py:49-76 (numpy version, the one the entry points call)."""
+    seg = np.asarray(seg)
+    n = seg.size
+    labels = list(np.unique(seg))
+    ratio = [np.float32((seg == l).sum()) / np.float32(n) for l in labels]
+    new = list(labels)
+    for i, l in enumerate(labels):
+        if ratio[i] < np.float32(min_ratio):
+            for j in range(table.shape[0]):
+                nl = table[j, l]
+                if nl in labels and ratio[labels.index(nl)] >= np.float32(min_ratio):
+                    new[i] = nl
+                    break
+    out = seg.copy()
+    for i, l in enumerate(labels):
+        out[seg == l] = new[i]
+    return out
+
+
+def seg_cross_remapping(content_seg, style_seg, table):
+    """ref: models/segmentation/SegReMapping.py:19-46."""
+    content_seg, style_seg = np.asarray(content_seg), np.asarray(style_seg)
+    cl, sl = list(np.unique(content_seg)), list(np.unique(style_seg))
+    new = list(cl)
+    for i, l in enumerate(cl):
+        if l in sl:
+            continue
+        for j in range(table.shape[0]):
+            nl = table[j, l]
+            if nl in sl:
+                new[i] = nl
+                break
+    out = content_seg.copy()
+    for i, l in enumerate(cl):
+        out[content_seg == l] = new[i]
+    return out
+
+
+SEG_COLOR_TABLE = [((0, 0, 255), 3), ((0, 255, 0), 2), ((0, 0, 0), 0), ((255, 255, 255), 1), ((255, 0, 0), 4),
+                   ((255, 255, 0), 5), ((128, 128, 128), 6), ((0, 255, 255), 7), ((255, 0, 255), 8)]
+
+
+def seg_labels_from_colors(rgb):
+    """ref: utils/utils.py:105-137 — exact table colour, else the nearest in L1; the first minimum in dict order wins."""
+    a = np.asarray(rgb).astype(np.int64)
+    best = np.full(a.shape[:2], 1 << 30, np.int64)
+    lab = np.zeros(a.shape[:2], np.uint8)
+    for col, l in SEG_COLOR_TABLE:
+        d = np.abs(a - np.array(col)).sum(-1)
+        m = d < best
+        best[m], lab[m] = d[m], l
+    return lab

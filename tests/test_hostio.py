@@ -34,3 +34,25 @@ def test_img_resize_matches_reference():
     img = Image.fromarray(g["img"])
     assert np.array_equal(np.array(img_resize(img, 40, down_scale=4)), g["resized_40"])
     assert np.array_equal(np.array(img_resize(img, 1280, down_scale=4)), g["resized_1280"])
+
+
+def test_oracle_seg_remapping_matches_reference():
+    """oracle.seg_self_remapping / seg_cross_remapping against vectors recorded from the reference's SegReMapping
+    (oracle/make_golden_seg.py, synthetic relation table)."""
+    from oracle import vst_oracle as O
+    g = load_golden("seg_remap.npz")
+    table = g["table"]
+    for k in range(3):
+        r = float(g["ratio%d" % k])
+        cs = O.seg_self_remapping(g["c%d" % k], table, r)
+        ss = O.seg_self_remapping(g["s%d" % k], table, r)
+        assert np.array_equal(cs, g["c_self%d" % k]) and np.array_equal(ss, g["s_self%d" % k])
+        assert np.array_equal(O.seg_cross_remapping(cs, ss, table), g["c_cross%d" % k])
+        assert not np.array_equal(cs, g["c%d" % k]) or k == 2            # the small labels really moved
+    h = load_golden("hostio.npz")
+    seg = h["seg"].astype(np.int32)
+    tab = np.array([c for c, _ in O.SEG_COLOR_TABLE], np.int32)
+    d = np.sort(np.abs(seg[:, :, None, :] - tab[None, None]).sum(-1), axis=-1)
+    unambiguous = d[..., 0] < d[..., 1]
+    assert np.array_equal(O.seg_labels_from_colors(h["seg"])[unambiguous], h["labels"][unambiguous])
+    assert np.array_equal(O.seg_labels_from_colors(h["seg"]), labels_from_colors(h["seg"]))

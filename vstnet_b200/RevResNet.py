@@ -236,6 +236,10 @@ class RevResNet(nn.Module):
                 ev.synchronize()
             if ev.query():
                 hit = hit or bool(int(host[0]) & 1)
+                if int(host[1]) < 0:             # fused frame path: the cWCT factorisation of that frame failed
+                    import warnings
+                    warnings.warn("vstnet_b200: a Cholesky factorisation did not succeed within 64 jitter retries; that "
+                                  "frame was returned unstylized", RuntimeWarning)
             else:
                 keep.append((ev, host))
         self._range_pending = keep
@@ -249,24 +253,29 @@ class RevResNet(nn.Module):
             self._range_fallback("in an earlier call, whose result is invalid")
         return hit
 
-    def _launch(self, fn, what, src, dst, B, H, W):
+    def _launch(self, fn, what, src, dst, B, H, W, call=None):
+        """Enqueue one pass (``fn`` = forward / inverse, or ``call(packed, ws, stream)`` for the fused frame path) on the
+        current stream and run the f16x2 range guard around it."""
         dev = src.device
         with torch.cuda.device(dev):
             while True:
                 packed, ws = self._packed_weights(dev), self._workspace(dev, B, H, W)
                 st = torch.cuda.current_stream(dev)
-                _lib.check(fn(self._h, packed.data_ptr(), src.data_ptr(), dst.data_ptr(), B, H, W, ws.data_ptr(),
-                              ws.numel(), st.cuda_stream), what)
-                if self._precision != "f16x2" or self.range_check == "off":
+                if call is not None:
+                    _lib.check(call(packed, ws, st.cuda_stream), what)
+                else:
+                    _lib.check(fn(self._h, packed.data_ptr(), src.data_ptr(), dst.data_ptr(), B, H, W, ws.data_ptr(),
+                                  ws.numel(), st.cuda_stream), what)
+                if (self._precision != "f16x2" and call is None) or self.range_check == "off":
                     return
-                if self._poll_range():
+                if self._poll_range() and self._precision == "f16x2":
                     self._range_fallback("in an earlier call, whose result is invalid")
                     return
-                host = torch.empty(1, dtype=torch.int32, pin_memory=True)
-                host.copy_(ws[:4].view(torch.int32), non_blocking=True)
+                host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+                host.copy_(ws[:16].view(torch.int32), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(st)
-                if self.range_check == "strict":
+                if self.range_check == "strict" and self._precision == "f16x2":
                     ev.synchronize()
                     if int(host[0]) & 1:
                         self._range_fallback("in this call; re-running it")
@@ -276,6 +285,47 @@ class RevResNet(nn.Module):
                     self._range_pending.pop(0)
                 self._range_pending.append((ev, host))
                 return
+
+    # ------------------------------------------------------------------ fused frame path (video)
+    def stylize_supported(self, H, W):
+        """True if ``stylize_frame`` can take an H x W frame (both reference modes; latent width >= 32)."""
+        return bool(self._lib.vst_revnet_stylize_supported(self._h, int(H), int(W)))
+
+    @torch.no_grad()
+    def stylize_frame(self, frame, style_stats, alpha_c=0.0, eps=2e-5, use_double=False, out=None, bgr=False):
+        """encode -> cWCT against hoisted style statistics -> decode as ONE native call that never materialises the
+        latent (``vst_revnet_stylize``): the statistics are taken from, and the transform applied to, the network's own
+        state.  ``frame``: fp32 CUDA ``[1,3,H,W]`` (returns fp32 ``[1,3,H,W]``) or uint8 CUDA ``[H,W,3]`` (returns uint8
+        ``[H,W,3]``, ``mul(255).clamp(0,255).byte()`` semantics).  ``style_stats``: a buffer of
+        ``cWCT.precompute_style(...)["stats"]``.  Equals ``self(cwct.transfer(self(frame), style), forward=False)`` up
+        to the summation order of the statistics (ref: video_transfer.py:192-206)."""
+        u8 = frame.dtype == torch.uint8
+        if not frame.is_cuda:
+            raise RuntimeError("vstnet_b200.RevResNet runs on CUDA (sm_100a) only; frame is on %s" % frame.device)
+        if u8:
+            if frame.dim() != 3 or frame.shape[2] != 3:
+                raise ValueError("uint8 frames must be [H,W,3]")
+            H, W = int(frame.shape[0]), int(frame.shape[1])
+        else:
+            self._check_input(frame, "frame")
+            if frame.shape[0] != 1 or frame.shape[1] != 3:
+                raise ValueError("fp32 frames must be [1,3,H,W]")
+            H, W = int(frame.shape[2]), int(frame.shape[3])
+        if not self.stylize_supported(H, W):
+            raise ValueError("the fused frame path does not support this configuration / size (%dx%d)" % (H, W))
+        frame = frame.contiguous()
+        if out is None:
+            out = torch.empty_like(frame)
+        elif out.shape != frame.shape or out.dtype != frame.dtype or not out.is_contiguous():
+            raise ValueError("out must be a contiguous tensor like frame")
+        lib, h = self._lib, self._h
+
+        def call(packed, ws, stream):
+            return lib.vst_revnet_stylize(h, packed.data_ptr(), frame.data_ptr(), out.data_ptr(), int(u8), int(bool(bgr)), H, W,
+                                          style_stats.data_ptr(), float(alpha_c), float(eps), int(bool(use_double)),
+                                          ws.data_ptr(), ws.numel(), stream)
+        self._launch(None, "vst_revnet_stylize", frame, out, 1, H, W, call=call)
+        return out
 
     @torch.no_grad()
     def _forward(self, x):

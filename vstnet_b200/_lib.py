@@ -58,6 +58,9 @@ SIGNATURES = {
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
     "vst_revnet_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "vst_revnet_stylize_supported": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vst_revnet_stylize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vst_cwct_stats_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vst_cwct_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vst_cwct_factor": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_float), C.c_int, C.c_float,
@@ -72,6 +75,10 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vst_frame_u8_to_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vst_mask_resize_nearest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vst_seg_scratch_bytes": (C.c_size_t, []),
+    "vst_seg_remap": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vst_seg_labels_from_colors": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "vst_frame_f32_to_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

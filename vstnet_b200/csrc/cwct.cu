@@ -52,6 +52,28 @@ __global__ void pivot_kernel(const float* __restrict__ feat, long long n, float*
     }
 }
 
+// the same for the latent that the P4 half-state x1 spreads to: channel c of sub-position 0 = state channel c of x1
+__global__ void pivot_state_kernel(const float* __restrict__ x1, int h, int w, float* __restrict__ pivot) {
+    const int c = blockIdx.x;
+    const long long n = (long long)h * w, S = n < 4096 ? n : 4096;
+    const float* plane = x1 + (size_t)(c >> 2) * p4_plane_px(h, w) * 4 + (c & 3);
+    float s = 0.f;
+    for (long long k = threadIdx.x; k < S; k += blockDim.x) {
+        const long long p = (k * n) / S;
+        const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+        s += __ldg(plane + ((size_t)(y + 1) * (w + 2) + x + 1) * 4);
+    }
+    __shared__ float red[32];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) pivot[c] = s / (float)S;
+    }
+}
+
 // ---- C <= 32: every warp owns a private 32x32 Gram in registers (lane: 4 rows x 8 cols) and
 // streams its own contiguous pixel range through a private smem sub-tile.  fp32 products are summed
 // in fp32 over runs of at most 256 pixels and folded into fp64; the unmasked kernel keeps the fp64
@@ -686,6 +708,125 @@ __global__ void __launch_bounds__(256) apply_kernel(const float* __restrict__ fe
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// apply on the P4 half-states, in place (fused video path: the latent is never materialised):
+//   for every state pixel p and sub-position j:  s[jC .. jC+C) <- T (s[jC .. jC+C) - mu) + beta
+// which is exactly spread -> apply -> gather (models/RevResNet.py:140-146, cWCT.py:147,161-162, RevResNet.py:149-152).
+// Tile = one sub-position x PX consecutive interior pixels; same thread tile (8 channels x 4 pixels, FFMA2) as above.
+// ------------------------------------------------------------------------------------------
+template <int CP>
+__global__ void __launch_bounds__(256) apply_state_kernel(float* __restrict__ x1, float* __restrict__ x2, int Ch, int h, int w,
+                                                          const float* __restrict__ T, const float* __restrict__ mu,
+                                                          const float* __restrict__ beta, const int* __restrict__ valid,
+                                                          int tiles_per_sub, int n_tiles) {
+    using Cfg = ApplyCfg<CP>;
+    constexpr int PX = Cfg::PX, NPG = Cfg::NPG, G = CP / 4;
+    if (!valid[0]) return;                  // factorisation failed: the content features pass through (cWCT.py:80-84)
+    extern __shared__ __align__(16) float smf[];
+    float* xs = smf;                   // [CP][PX]
+    float* Tt = xs + CP * PX;          // [k][c] (transposed)
+    float* mu_s = Tt + CP * CP;        // [CP]
+    float* be_s = mu_s + CP;           // [CP]
+    const int tid = threadIdx.x;
+    const int pg = tid % NPG, cg = tid / NPG;
+    const int n_px = h * w, Wp = w + 2, gph = Ch / 4;
+    const size_t plane = p4_plane_px(h, w);
+    for (int i = tid; i < CP * CP; i += 256) {
+        const int k = i / CP, c = i - k * CP;     // Tt[k][c] = T[c][k]
+        Tt[i] = __ldg(T + (size_t)c * CP + k);
+    }
+    for (int i = tid; i < CP; i += 256) { mu_s[i] = mu[i]; be_s[i] = beta[i]; }
+
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int j = t / tiles_per_sub, p0 = (t - j * tiles_per_sub) * PX;
+        const int npx = min(PX, n_px - p0);
+        const int g0 = j * G;                                           // first state group of this sub-position
+        float4* base = reinterpret_cast<float4*>(g0 < gph ? x1 : x2) + (size_t)(g0 < gph ? g0 : g0 - gph) * plane;
+        __syncthreads();   // previous tile's smem fully consumed (and Tt staged)
+        for (int i = tid; i < G * PX; i += 256) {
+            const int g = i / PX, px = i - g * PX;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (px < npx) {
+                const int p = p0 + px, y = p / w, x = p - y * w;
+                v = base[(size_t)g * plane + (size_t)(y + 1) * Wp + x + 1];
+            }
+            xs[(4 * g + 0) * PX + px] = v.x; xs[(4 * g + 1) * PX + px] = v.y;
+            xs[(4 * g + 2) * PX + px] = v.z; xs[(4 * g + 3) * PX + px] = v.w;
+        }
+        __syncthreads();
+        float acc[8][4];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        // this thread's 4 pixels are pg, pg + NPG, pg + 2 NPG, pg + 3 NPG: consecutive lanes own consecutive pixels, so
+        // the 16-byte P4 stores below are contiguous across the warp (4 pixels per lane would write half-used sectors)
+#pragma unroll 4
+        for (int k = 0; k < CP; ++k) {
+            const float* xr = xs + k * PX + pg;
+            const float4 t0 = *reinterpret_cast<const float4*>(Tt + k * CP + cg * 8);
+            const float4 t1 = *reinterpret_cast<const float4*>(Tt + k * CP + cg * 8 + 4);
+            const float m = mu_s[k];
+            const float xv[4] = {xr[0] - m, xr[NPG] - m, xr[2 * NPG] - m, xr[3 * NPG] - m};
+            const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                fma2(acc[a][0], acc[a][1], tv[a], xv[0], xv[1]);
+                fma2(acc[a][2], acc[a][3], tv[a], xv[2], xv[3]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int px = pg + b * NPG;
+            if (px >= npx) continue;
+            const int p = p0 + px, y = p / w, x = p - y * w;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int c = cg * 8 + half * 4;
+                const float4 o = make_float4(acc[half * 4 + 0][b] + be_s[c], acc[half * 4 + 1][b] + be_s[c + 1],
+                                             acc[half * 4 + 2][b] + be_s[c + 2], acc[half * 4 + 3][b] + be_s[c + 3]);
+                p4_store(base + (size_t)(c >> 2) * plane, h, w, y, x, o);
+            }
+        }
+    }
+}
+
+template <int CP>
+static int launch_apply_state_cfg(float* x1, float* x2, int Ch, int h, int w, const float* T, const float* mu,
+                                  const float* beta, const int* valid, cudaStream_t st) {
+    using Cfg = ApplyCfg<CP>;
+    static PerDeviceOnce smem_once;
+    auto kern = apply_state_kernel<CP>;
+    VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
+    const int nsub = 2 * Ch / CP;
+    const int tiles_per_sub = cdiv((long long)h * w, Cfg::PX), n_tiles = nsub * tiles_per_sub;
+    const int grid = std::min(n_tiles, num_sms() * (CP == 32 ? 6 : 2));
+    const double n = (double)nsub * h * w;
+    ProfScope prof(st, CP == 32 ? "cwct_apply_state c32" : "cwct_apply_state c128", 2.0 * CP * CP * n, 8.0 * CP * n);
+    kern<<<grid, 256, Cfg::SMEM, st>>>(x1, x2, Ch, h, w, T, mu, beta, valid, tiles_per_sub, n_tiles);
+    return check_launch("cwct_apply_state");
+}
+
+// in-place transform of the latent held as P4 half-states x1 | x2 (Ch channels each), C latent channels, label 0
+int launch_apply_state(float* x1, float* x2, int C, int Ch, int h, int w, const float* T, const float* mu, const float* beta,
+                       const int* valid, cudaStream_t st) {
+    VST_REQUIRE(C == 32 || C == 128, "apply_state: C = %d not supported", C);
+    if (C == 32) return launch_apply_state_cfg<32>(x1, x2, Ch, h, w, T, mu, beta, valid, st);
+    return launch_apply_state_cfg<128>(x1, x2, Ch, h, w, T, mu, beta, valid, st);
+}
+
+// statistics of that latent (one label): zero-initialises `stats`, pivot from sub-position 0, tensor-core Gram
+int launch_stats_state(const float* x1, const float* x2, int C, int Ch, int h, int w, void* stats, cudaStream_t st) {
+    StatsView sv = stats_view(stats, C, 1);
+    VST_CUDA_OK(cudaMemsetAsync(stats, 0, stats_doubles(C, 1) * sizeof(double), st));
+    count_launch();
+    pivot_state_kernel<<<C, 256, 0, st>>>(x1, h, w, sv.pivot);
+    if (check_launch("cwct_pivot_state")) return 1;
+    const double n = (double)(2 * Ch / C) * h * w;
+    ProfScope prof(st, C <= 32 ? "cwct_gram_state c32" : "cwct_gram_state c128", 2.0 * C * C * n, 4.0 * C * n);
+    return launch_gram_tc_state(x1, x2, sv.pivot, sv.count, sv.sum, sv.gram, C, Ch, h, w, st);
+}
+
 template <int CP>
 static int launch_apply(const float* feat, float* out, int C, long long n, const uint8_t* labels, int L, const float* T,
                         const float* mu, const float* beta, const int* valid, cudaStream_t st) {
@@ -748,7 +889,10 @@ extern "C" int vst_cwct_stats(const float* feat, int C, long long n, const uint8
     return check_launch("cwct_gram");
 }
 
-static int launch_factor(int mode, const void* content_stats, const void* const* style_stats, const float* alpha_s,
+namespace vst {
+size_t cwct_stats_bytes(int C, int n_labels) { return align_up(stats_doubles(C, n_labels) * sizeof(double) + (size_t)C * sizeof(float), 16); }
+
+int launch_factor(int mode, const void* content_stats, const void* const* style_stats, const float* alpha_s,
                          int n_styles, float alpha_c, float eps, int C, int n_labels, int masked, int use_double, float* T,
                          float* mu, float* beta, int* valid, int* status, cudaStream_t st) {
     VST_REQUIRE(T && mu && beta && valid && status, "vst_cwct_factor: null output");
@@ -776,6 +920,7 @@ static int launch_factor(int mode, const void* content_stats, const void* const*
     factor_kernel<<<n_labels, 256, smem, st>>>(fa);
     return check_launch("cwct_factor");
 }
+}  // namespace vst
 
 extern "C" int vst_cwct_factor(const void* content_stats, const void* const* style_stats, const float* alpha_s,
                                int n_styles, float alpha_c, float eps, int C, int n_labels, int masked, int use_double,

@@ -181,10 +181,24 @@ int launch_pack_tch_s2_weights(const float* w, float* wp, int C, int Cout, cudaS
 bool gram_tc_eligible(int C, long long n);
 int launch_gram_tc(const float* feat, const float* pivot, double* count, double* sum, double* gram, int C, long long n,
                    cudaStream_t st);
+// ... of the latent that the P4 half-states x1 | x2 (Ch channels each, h x w) spread to, without materialising it
+int launch_gram_tc_state(const float* x1, const float* x2, const float* pivot, double* count, double* sum, double* gram, int C,
+                         int Ch, int h, int w, cudaStream_t st);
+
+// cWCT on the network's own state (fused video path), cwct.cu
+int launch_stats_state(const float* x1, const float* x2, int C, int Ch, int h, int w, void* stats, cudaStream_t st);
+int launch_apply_state(float* x1, float* x2, int C, int Ch, int h, int w, const float* T, const float* mu, const float* beta,
+                       const int* valid, cudaStream_t st);
+int launch_factor(int mode, const void* content_stats, const void* const* style_stats, const float* alpha_s, int n_styles,
+                  float alpha_c, float eps, int C, int n_labels, int masked, int use_double, float* T, float* mu, float* beta,
+                  int* valid, int* status, cudaStream_t st);
+size_t cwct_stats_bytes(int C, int n_labels);
 
 // layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
 int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, cudaStream_t st);   // NCHW -> P4
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st);           // P4 -> NCHW
+int launch_image_u8_to_state(const uint8_t* hwc, float* s0, int C0, int H, int W, int bgr, int* status_clear, cudaStream_t st);
+int launch_state_to_image_u8(const float* s0, uint8_t* hwc, int H, int W, int bgr, cudaStream_t st);
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st);
 int launch_p4_replicate_topleft(float* t, int C, int H, int W, cudaStream_t st);
 int launch_depth_to_space(const float* in, float* out, int Cout, int Hin, int Win, cudaStream_t st);

@@ -40,6 +40,52 @@ __global__ void state_to_image_kernel(const float4* __restrict__ s0, float* __re
     }
 }
 
+// The same straight from / to the video frame format, uint8 HWC (RGB or BGR): ToTensor's byte / 255 and the
+// mul(255).clamp(0,255).byte() truncation of video_transfer.py:188, :211-214 folded into the first / last kernel of the
+// pass (bit-identical to vst_frame_u8_to_f32 / vst_frame_f32_to_u8 around the fp32 kernels).
+__global__ void image_u8_to_state_kernel(const uint8_t* __restrict__ hwc, float4* __restrict__ s0, int G, int H, int W, int bgr,
+                                         int* __restrict__ status_clear) {
+    if (status_clear && blockIdx.x == 0 && threadIdx.x == 0) *status_clear = 0;
+    const size_t n = (size_t)H * W, total = (size_t)G * n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / n);
+        const size_t p = i - (size_t)g * n;
+        const int y = (int)(p / W), xx = (int)(p - (size_t)y * W);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g == 0) {
+            const uint8_t* px = hwc + p * 3;
+            const float r = (float)px[bgr ? 2 : 0] / 255.f, gg = (float)px[1] / 255.f, b = (float)px[bgr ? 0 : 2] / 255.f;
+            v = make_float4(r, gg, b, 0.f);
+        }
+        p4_store(s0 + (size_t)g * p4_plane_px(H, W), H, W, y, xx, v);
+    }
+}
+__global__ void state_to_image_u8_kernel(const float4* __restrict__ s0, uint8_t* __restrict__ hwc, int H, int W, int bgr) {
+    const size_t n = (size_t)H * W;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(p / W), xx = (int)(p - (size_t)y * W);
+        const float4 v = __ldg(s0 + (size_t)(y + 1) * (W + 2) + xx + 1);
+        const float e[3] = {v.x, v.y, v.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float q = fminf(fmaxf(e[c] * 255.f, 0.f), 255.f);        // mul(255).clamp(0,255)
+            hwc[p * 3 + (bgr ? 2 - c : c)] = (uint8_t)q;                     // .byte() truncates
+        }
+    }
+}
+int launch_image_u8_to_state(const uint8_t* hwc, float* s0, int C0, int H, int W, int bgr, int* status_clear, cudaStream_t st) {
+    const size_t total = (size_t)(C0 / 4) * H * W;
+    ProfScope prof(st, "image_u8_to_state", 0.0, 3.0 * H * W + 16.0 * total);
+    image_u8_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(hwc, reinterpret_cast<float4*>(s0), C0 / 4, H, W, bgr, status_clear);
+    return check_launch("image_u8_to_state");
+}
+int launch_state_to_image_u8(const float* s0, uint8_t* hwc, int H, int W, int bgr, cudaStream_t st) {
+    const size_t total = (size_t)H * W;
+    ProfScope prof(st, "state_to_image_u8", 0.0, 16.0 * total + 3.0 * total);
+    state_to_image_u8_kernel<<<ew_grid(total), 256, 0, st>>>(reinterpret_cast<const float4*>(s0), hwc, H, W, bgr);
+    return check_launch("state_to_image_u8");
+}
+
 int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, cudaStream_t st) {
     const size_t total = (size_t)(C0 / 4) * H * W;
     ProfScope prof(st, "image_to_state", 0.0, 4.0 * Cimg * H * W + 16.0 * total);
@@ -320,4 +366,129 @@ extern "C" int vst_frame_f32_to_u8(const float* chw, uint8_t* hwc, int H, int W,
     int n = H * W;
     f32_to_u8_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(chw, hwc, n, bgr);
     return check_launch("f32_to_u8");
+}
+
+// ------------------------------------------------------------------------------------------
+// Mask preparation on the device: label histogram, the label re-mapping of
+// models/segmentation/SegReMapping.py:19-76 (self_remapping / cross_remapping) as a 256-entry look-up table built by
+// one small CTA, and the colour -> label rule of utils/utils.py:105-137 (load_segment).  No host round trip: the
+// reference's np.unique / per-label boolean masks / per-pixel Python loop become three streaming kernels.
+// ------------------------------------------------------------------------------------------
+namespace vst {
+
+__global__ void seg_hist_kernel(const uint8_t* __restrict__ seg, long long n, unsigned int* __restrict__ counts) {
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0;                                     // blockDim.x == 256
+    __syncthreads();
+    const long long n16 = n / 16;
+    const uint4* s16 = reinterpret_cast<const uint4*>(seg);
+    const bool aligned = ((uintptr_t)seg & 15) == 0;
+    if (aligned) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+            const uint4 v = __ldg(s16 + i);
+            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) atomicAdd(&h[(w[k] >> (8 * b)) & 255u], 1u);
+        }
+    }
+    for (long long i = (aligned ? n16 * 16 : 0) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&h[seg[i]], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+// mode 0: self_remapping  — a label whose pixel ratio is below min_ratio moves to the first label of its column of the
+//         relation table that is present with a ratio >= min_ratio (SegReMapping.py:49-76)
+// mode 1: cross_remapping — a content label absent from the style moves to the first label of its column that the
+//         style has (SegReMapping.py:19-46).  counts_a: the map being re-labelled, counts_b: the style map (mode 1).
+__global__ void seg_lut_kernel(const unsigned int* __restrict__ counts_a, const unsigned int* __restrict__ counts_b,
+                               long long n_a, const int* __restrict__ mapping, int rows, int n_classes, float min_ratio,
+                               int mode, uint8_t* __restrict__ lut) {
+    const int l = threadIdx.x;                              // one thread per label, 256 threads
+    int out = l;
+    const unsigned int ca = counts_a[l];
+    if (ca > 0 && l < n_classes) {
+        if (mode == 0) {
+            const float nf = (float)n_a;
+            if ((float)ca / nf < min_ratio) {
+                for (int j = 0; j < rows; ++j) {
+                    const int nl = mapping[(size_t)j * n_classes + l];
+                    if (nl >= 0 && nl < 256 && counts_a[nl] > 0 && (float)counts_a[nl] / nf >= min_ratio) { out = nl; break; }
+                }
+            }
+        } else if (counts_b[l] == 0) {
+            for (int j = 0; j < rows; ++j) {
+                const int nl = mapping[(size_t)j * n_classes + l];
+                if (nl >= 0 && nl < 256 && counts_b[nl] > 0) { out = nl; break; }
+            }
+        }
+    }
+    lut[l] = (uint8_t)out;
+}
+
+__global__ void seg_apply_lut_kernel(const uint8_t* __restrict__ seg, long long n, const uint8_t* __restrict__ lut_g,
+                                     uint8_t* __restrict__ out) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = lut_g[threadIdx.x];                  // blockDim.x == 256
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = lut[seg[i]];
+}
+
+// nearest table colour in L1, the first strict minimum in the reference's dict order winning ties
+// (utils/utils.py:106-137: the tie branch there always raises inside its try and leaves the first minimum in place)
+__global__ void seg_labels_from_colors_kernel(const uint8_t* __restrict__ rgb, long long n, uint8_t* __restrict__ labels) {
+    const int tab[9][4] = {{0, 0, 255, 3}, {0, 255, 0, 2}, {0, 0, 0, 0}, {255, 255, 255, 1}, {255, 0, 0, 4}, {255, 255, 0, 5},
+                           {128, 128, 128, 6}, {0, 255, 255, 7}, {255, 0, 255, 8}};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = rgb[3 * i], g = rgb[3 * i + 1], b = rgb[3 * i + 2];
+        int best = 99999, lab = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int d = abs(r - tab[k][0]) + abs(g - tab[k][1]) + abs(b - tab[k][2]);
+            if (d < best) { best = d; lab = tab[k][3]; }
+        }
+        labels[i] = (uint8_t)lab;
+    }
+}
+
+static int seg_grid(long long n) { return (int)std::min<long long>((n + 4095) / 4096 + 1, (long long)num_sms() * 8); }
+
+}  // namespace vst
+
+extern "C" size_t vst_seg_scratch_bytes(void) { return 2 * 256 * sizeof(unsigned int) + 256; }
+
+extern "C" int vst_seg_remap(const uint8_t* seg, long long n, const uint8_t* style_seg, long long n_style, const int* mapping,
+                             int rows, int n_classes, float min_ratio, uint8_t* out, void* scratch, void* stream) {
+    using namespace vst;
+    VST_REQUIRE(seg && out && mapping && scratch && n > 0 && rows > 0 && n_classes > 0 && n_classes <= 256,
+                "vst_seg_remap: bad arguments");
+    VST_REQUIRE(((uintptr_t)scratch & 3) == 0, "vst_seg_remap: scratch must be 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* ca = (unsigned int*)scratch;
+    unsigned int* cb = ca + 256;
+    uint8_t* lut = (uint8_t*)(cb + 256);
+    VST_CUDA_OK(cudaMemsetAsync(scratch, 0, 2 * 256 * sizeof(unsigned int), st));
+    count_launch();
+    seg_hist_kernel<<<seg_grid(n), 256, 0, st>>>(seg, n, ca);
+    if (check_launch("seg_hist")) return 1;
+    if (style_seg) {
+        VST_REQUIRE(n_style > 0, "vst_seg_remap: empty style map");
+        seg_hist_kernel<<<seg_grid(n_style), 256, 0, st>>>(style_seg, n_style, cb);
+        if (check_launch("seg_hist")) return 1;
+    }
+    seg_lut_kernel<<<1, 256, 0, st>>>(ca, cb, n, mapping, rows, n_classes, min_ratio, style_seg ? 1 : 0, lut);
+    if (check_launch("seg_lut")) return 1;
+    seg_apply_lut_kernel<<<seg_grid(n), 256, 0, st>>>(seg, n, lut, out);
+    return check_launch("seg_apply_lut");
+}
+
+extern "C" int vst_seg_labels_from_colors(const uint8_t* rgb_hwc, long long n, uint8_t* labels, void* stream) {
+    using namespace vst;
+    VST_REQUIRE(rgb_hwc && labels && n > 0, "vst_seg_labels_from_colors: bad arguments");
+    seg_labels_from_colors_kernel<<<seg_grid(n), 256, 0, (cudaStream_t)stream>>>(rgb_hwc, n, labels);
+    return check_launch("seg_labels_from_colors");
 }

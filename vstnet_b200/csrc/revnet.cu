@@ -90,12 +90,19 @@ static bool block_fused_tc(const vst_revnet* n, const BlockDesc& b) {
 struct Shape { int c, h, w; };
 
 struct Workspace {
-    int* status;     // first 64 bytes of the workspace: [0] status bits of the last call (VST_STATUS_*)
+    int* status;     // first 64 bytes of the workspace: [0] status bits of the last call (VST_STATUS_*),
+                     // [1] cWCT Cholesky retries (-1: failed) and [2] cWCT validity of the last fused stylize call
+    uint8_t* cstats; // cWCT scratch of the fused path: content statistics block (one label) ...
+    float *T, *mu, *beta;   // ... and the transform
     float* P[3];
     float* T1;
     float* T2;
 };
 constexpr size_t WS_HEADER_FLOATS = 16;
+static size_t cwct_scratch_floats(const vst_revnet* n) {
+    const int C = 2 * n->cfg.hidden_dim;
+    return align_up(cwct_stats_bytes(C, 1) / 4 + (size_t)C * C + 2 * (size_t)C + 16, 64);
+}
 
 static size_t half_state_floats(const vst_revnet* n, int H, int W) {
     // largest half-state over all stages, in the P4 layout (border + slack included)
@@ -122,11 +129,20 @@ static size_t temp_floats(const vst_revnet* n, int H, int W) {
 
 static int carve(const vst_revnet* n, int H, int W, void* ws, size_t ws_bytes, Workspace* out) {
     size_t hs = half_state_floats(n, H, W), ts = temp_floats(n, H, W);
-    size_t need = (WS_HEADER_FLOATS + 3 * hs + 2 * ts) * sizeof(float);
+    size_t need = (WS_HEADER_FLOATS + cwct_scratch_floats(n) + 3 * hs + 2 * ts) * sizeof(float);
     VST_REQUIRE(ws != nullptr && ws_bytes >= need, "workspace too small: have %zu bytes, need %zu", ws_bytes, need);
     VST_REQUIRE(((uintptr_t)ws & 15) == 0, "workspace must be 16-byte aligned");
     float* p = (float*)ws;
     out->status = (int*)p; p += WS_HEADER_FLOATS;
+    {
+        const int C = 2 * n->cfg.hidden_dim;
+        float* q = p;
+        out->cstats = (uint8_t*)q; q += cwct_stats_bytes(C, 1) / 4;
+        out->T = q; q += (size_t)C * C;
+        out->mu = q; q += C;
+        out->beta = q;
+        p += cwct_scratch_floats(n);
+    }
     for (int i = 0; i < 3; ++i) { out->P[i] = p; p += hs; }
     out->T1 = p; p += ts;
     out->T2 = p;
@@ -217,11 +233,20 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
     return 0;
 }
 
-static int forward_one(const vst_revnet* n, const float* packed, const float* x, float* z, int H, int W,
-                       const Workspace& ws, bool first, cudaStream_t st) {
+// the two half-states of the network between encode and decode (what channel_reduction's spread loops turn into z)
+struct StatePair { float *s0, *s1, *spare; int h, w; };
+
+// frame source / sink of a pass: fp32 NCHW (the reference API) or uint8 HWC (the video frame format)
+struct FrameIO { const float* f32_in; const uint8_t* u8_in; float* f32_out; uint8_t* u8_out; int bgr; };
+
+static int encode_state(const vst_revnet* n, const float* packed, const FrameIO& io, int H, int W, const Workspace& ws,
+                        bool first, cudaStream_t st, StatePair* sp) {
     float *s0 = ws.P[0], *s1 = ws.P[1], *spare = ws.P[2];
     // injective_pad + split (RevResNet.py:24-28, :8-12): s0 = [x, 0...], s1 = 0
-    if (launch_image_to_state(x, s0, n->cfg.in_channel, n->c0, H, W, first ? ws.status : nullptr, st)) return 1;
+    if (io.u8_in) {
+        VST_REQUIRE(n->cfg.in_channel == 3, "uint8 frames have 3 channels");
+        if (launch_image_u8_to_state(io.u8_in, s0, n->c0, H, W, io.bgr, first ? ws.status : nullptr, st)) return 1;
+    } else if (launch_image_to_state(io.f32_in, s0, n->cfg.in_channel, n->c0, H, W, first ? ws.status : nullptr, st)) return 1;
     VST_CUDA_OK(cudaMemsetAsync(s1, 0, p4_floats(n->c0, H, W) * sizeof(float), st));
     count_launch(1);
 
@@ -260,14 +285,22 @@ static int forward_one(const vst_revnet* n, const float* packed, const float* x,
         if (run_F(n, b, packed, s1, h, w, ws, s0, s0, EPI_ADD, st)) return 1;
         std::swap(s0, s1);
     }
-    return launch_latent_spread(s0, s1, z, n->cr_channel, h, w, n->cfg.sp_steps, st);
+    sp->s0 = s0; sp->s1 = s1; sp->spare = spare; sp->h = h; sp->w = w;
+    return 0;
 }
 
-static int inverse_one(const vst_revnet* n, const float* packed, const float* z, float* x, int H, int W,
+static int forward_one(const vst_revnet* n, const float* packed, const float* x, float* z, int H, int W,
                        const Workspace& ws, bool first, cudaStream_t st) {
-    float *s0 = ws.P[0], *s1 = ws.P[1], *spare = ws.P[2];
-    int h = H / n->down, w = W / n->down;
-    if (launch_latent_gather(z, s0, s1, n->cr_channel, h, w, n->cfg.sp_steps, first ? ws.status : nullptr, st)) return 1;
+    StatePair sp;
+    FrameIO io = {x, nullptr, nullptr, nullptr, 0};
+    if (encode_state(n, packed, io, H, W, ws, first, st, &sp)) return 1;
+    return launch_latent_spread(sp.s0, sp.s1, z, n->cr_channel, sp.h, sp.w, n->cfg.sp_steps, st);
+}
+
+static int decode_state(const vst_revnet* n, const float* packed, StatePair sp, const FrameIO& io, int H, int W,
+                        const Workspace& ws, cudaStream_t st) {
+    float *s0 = sp.s0, *s1 = sp.s1, *spare = sp.spare;
+    int h = sp.h, w = sp.w;
     for (int i = (int)n->cr.size() - 1; i >= 0; --i) {
         if (run_F(n, n->cr[i], packed, s0, h, w, ws, s1, s1, EPI_SUB, st)) return 1;
         std::swap(s0, s1);
@@ -290,7 +323,22 @@ static int inverse_one(const vst_revnet* n, const float* packed, const float* z,
         }
     }
     // merge + injective_pad.inverse (RevResNet.py:30-31): keep the first in_channel channels of x1
-    return launch_state_to_image(s0, x, n->cfg.in_channel, H, W, st);
+    if (io.u8_out) return launch_state_to_image_u8(s0, io.u8_out, H, W, io.bgr, st);
+    return launch_state_to_image(s0, io.f32_out, n->cfg.in_channel, H, W, st);
+}
+
+static int inverse_one(const vst_revnet* n, const float* packed, const float* z, float* x, int H, int W,
+                       const Workspace& ws, bool first, cudaStream_t st) {
+    StatePair sp = {ws.P[0], ws.P[1], ws.P[2], H / n->down, W / n->down};
+    if (launch_latent_gather(z, sp.s0, sp.s1, n->cr_channel, sp.h, sp.w, n->cfg.sp_steps, first ? ws.status : nullptr, st))
+        return 1;
+    FrameIO io = {nullptr, nullptr, x, nullptr, 0};
+    return decode_state(n, packed, sp, io, H, W, ws, st);
+}
+
+__global__ void stylize_status_kernel(const int* __restrict__ valid_status, int* __restrict__ ws_status) {
+    ws_status[1] = valid_status[1];      // Cholesky retries (-1: failed)
+    ws_status[2] = valid_status[0];      // validity
 }
 
 }  // namespace vst
@@ -393,7 +441,7 @@ extern "C" int vst_revnet_pack_weights(const vst_revnet* net, const float* raw, 
 extern "C" size_t vst_revnet_workspace_bytes(const vst_revnet* net, int B, int H, int W) {
     (void)B;
     if (!net || H <= 0 || W <= 0) return 0;
-    return (WS_HEADER_FLOATS + 3 * half_state_floats(net, H, W) + 2 * temp_floats(net, H, W)) * sizeof(float);
+    return (WS_HEADER_FLOATS + cwct_scratch_floats(net) + 3 * half_state_floats(net, H, W) + 2 * temp_floats(net, H, W)) * sizeof(float);
 }
 
 static int check_hw(const vst_revnet* net, int B, int H, int W) {
@@ -416,6 +464,44 @@ extern "C" int vst_revnet_forward(const vst_revnet* net, const void* packed, con
     for (int b = 0; b < B; ++b)
         if (forward_one(net, (const float*)packed, x + b * xs, z + b * zs, H, W, ws, b == 0, (cudaStream_t)stream)) return 1;
     return 0;
+}
+
+static bool stylize_fused_ok(const vst_revnet* net, int H, int W) {
+    const int C = 2 * net->cfg.hidden_dim;
+    return (C == 32 || C == 128) && net->cr_channel % 128 == 0 && W / net->down >= 32 && net->cfg.in_channel == 3;
+}
+
+extern "C" int vst_revnet_stylize_supported(const vst_revnet* net, int H, int W) {
+    return net && H > 0 && W > 0 && H % net->down == 0 && W % net->down == 0 && stylize_fused_ok(net, H, W) ? 1 : 0;
+}
+
+extern "C" int vst_revnet_stylize(const vst_revnet* net, const void* packed, const void* frame_in, void* frame_out, int io_u8,
+                                  int bgr, int H, int W, const void* style_stats, float alpha_c, float eps, int use_double,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    VST_REQUIRE(net && packed && frame_in && frame_out && style_stats, "vst_revnet_stylize: null argument");
+    if (int r = check_hw(net, 1, H, W)) return r;
+    VST_REQUIRE(stylize_fused_ok(net, H, W), "vst_revnet_stylize: configuration not supported by the fused path "
+                                             "(latent channels 32 or 128, latent width >= 32)");
+    Workspace ws;
+    if (int r = carve(net, H, W, workspace, workspace_bytes, &ws)) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* pk = (const float*)packed;
+    const int C = 2 * net->cfg.hidden_dim;
+    FrameIO io = {io_u8 ? nullptr : (const float*)frame_in, io_u8 ? (const uint8_t*)frame_in : nullptr,
+                  io_u8 ? nullptr : (float*)frame_out, io_u8 ? (uint8_t*)frame_out : nullptr, bgr};
+    StatePair sp;
+    if (encode_state(net, pk, io, H, W, ws, true, st, &sp)) return 1;      // (its first kernel clears status word 0)
+    // cWCT on the state: statistics (tensor-core Gram over the P4 half-states), factor, in-place apply
+    if (launch_stats_state(sp.s0, sp.s1, C, net->cr_channel, sp.h, sp.w, ws.cstats, st)) return 1;
+    const void* ss[1] = {style_stats};
+    const float one[1] = {1.f};
+    int* vs = ws.status + 4;             // [4] valid, [5] status of the factor kernel
+    if (launch_factor(0, ws.cstats, ss, one, 1, alpha_c, eps, C, 1, 0, use_double, ws.T, ws.mu, ws.beta, vs, vs + 1, st))
+        return 1;
+    stylize_status_kernel<<<1, 1, 0, st>>>(vs, ws.status);
+    if (check_launch("stylize_status")) return 1;
+    if (launch_apply_state(sp.s0, sp.s1, C, net->cr_channel, sp.h, sp.w, ws.T, ws.mu, ws.beta, vs, st)) return 1;
+    return decode_state(net, pk, sp, io, H, W, ws, st);
 }
 
 extern "C" int vst_revnet_inverse(const vst_revnet* net, const void* packed, const float* z, float* x, int B, int H,

@@ -49,14 +49,19 @@ def labels_from_colors(rgb):
     return order[np.argmin(d[:, :, order], axis=-1)].astype(np.uint8)
 
 
-def load_segment(image_path, size=None):
-    """ref: utils/utils.py:104-153.  ``size`` = (w, h) nearest-neighbour resize before labelling."""
+def load_segment(image_path, size=None, device=None):
+    """ref: utils/utils.py:104-153.  ``size`` = (w, h) nearest-neighbour resize before labelling.  With ``device`` the
+    colour -> label step runs on the GPU (``vstnet_b200.segmentation.labels_from_colors``) and a uint8 CUDA tensor is
+    returned, which ``cWCT.transfer`` takes as it is; otherwise the vectorised numpy rule below."""
     if not os.path.exists(image_path):
         print("Can not find image path: %s " % image_path)
         return None
     image = Image.open(image_path).convert("RGB")
     if size is not None:
         image = image.resize((size[0], size[1]), Image.NEAREST)
+    if device is not None:
+        from .segmentation import labels_from_colors as device_labels
+        return device_labels(np.array(image), device)
     return labels_from_colors(np.array(image))
 
 

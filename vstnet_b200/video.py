@@ -135,6 +135,7 @@ class VideoStylizer:
         self.cwct = cwct if cwct is not None else cWCT()
         self.alpha_c = alpha_c
         self.style_pre = None
+        self.fused = True               # unmasked frames take the fused native call (vst_revnet_stylize)
         self._lib = _lib.load()
         self._pin = {}
 
@@ -168,10 +169,20 @@ class VideoStylizer:
     def stylize(self, content, content_seg=None):
         """content: fp32 CUDA [1,3,H,W] in [0,1] -> stylized fp32 CUDA [1,3,H,W]
         (encode -> cWCT vs hoisted style -> decode; ref: video_transfer.py:192-206)."""
-        z = self.net(content, forward=True)
         a = 0.0 if self.alpha_c is None else float(self.alpha_c)
+        if self._fused_ok(content, content_seg):
+            # one native call, the latent never leaves the network's state (vst_revnet_stylize)
+            return self.net.stylize_frame(content, self.style_pre["stats"][0], a, self.cwct.eps, self.cwct.use_double)
+        z = self.net(content, forward=True)
         zcs = self.cwct.transfer_precomputed(z, self.style_pre, content_seg, a, out=z)
         return self.net(zcs, forward=False)
+
+    def _fused_ok(self, frame, content_seg=None):
+        if not self.fused or content_seg is not None or self.style_pre["masked"] or len(self.style_pre["stats"]) != 1:
+            return False
+        if frame.dtype == torch.uint8:
+            return frame.dim() == 3 and self.net.stylize_supported(frame.shape[0], frame.shape[1])
+        return frame.dim() == 4 and frame.shape[0] == 1 and self.net.stylize_supported(frame.shape[2], frame.shape[3])
 
     @torch.no_grad()
     def stylize_frames(self, frames, content_segs=None):
@@ -224,6 +235,15 @@ class VideoStylizer:
         video_transfer.py:211-214).  H2D and D2H copies are part of the call."""
         dev = next(self.net.parameters()).device
         st = torch.cuda.current_stream(dev)
+        if frame.dtype == torch.uint8 and content_seg is None:
+            u8 = frame.contiguous().to(dev, non_blocking=True)
+            if self._fused_ok(u8):
+                a = 0.0 if self.alpha_c is None else float(self.alpha_c)
+                o = self.net.stylize_frame(u8, self.style_pre["stats"][0], a, self.cwct.eps, self.cwct.use_double, bgr=bgr)
+                host = self._pinned("out", tuple(o.shape), torch.uint8)
+                host.copy_(o, non_blocking=True)
+                st.synchronize()
+                return host
         if frame.dtype == torch.uint8:
             H, W = frame.shape[0], frame.shape[1]
             u8 = frame.contiguous().to(dev, non_blocking=True)
@@ -292,12 +312,18 @@ class VideoStylizer:
             if i >= R:
                 c.wait_event(ev_out[(i - R) % RH])         # frame i-R's download has left dout[b]
             with torch.cuda.stream(c):
-                x = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
-                _lib.check(self._lib.vst_frame_u8_to_f32(din[b].data_ptr(), x.data_ptr(), H, W, int(bgr), c.cuda_stream),
-                           "vst_frame_u8_to_f32")
-                y = self.stylize(x)
-                _lib.check(self._lib.vst_frame_f32_to_u8(y.data_ptr(), dout[b].data_ptr(), H, W, int(bgr), c.cuda_stream),
-                           "vst_frame_f32_to_u8")
+                if self._fused_ok(din[b]):
+                    # uint8 frame in, uint8 frame out: the format conversions live in the first / last kernel of the pass
+                    a = 0.0 if self.alpha_c is None else float(self.alpha_c)
+                    self.net.stylize_frame(din[b], self.style_pre["stats"][0], a, self.cwct.eps, self.cwct.use_double,
+                                           out=dout[b], bgr=bgr)
+                else:
+                    x = torch.empty(1, 3, H, W, dtype=torch.float32, device=dev)
+                    _lib.check(self._lib.vst_frame_u8_to_f32(din[b].data_ptr(), x.data_ptr(), H, W, int(bgr), c.cuda_stream),
+                               "vst_frame_u8_to_f32")
+                    y = self.stylize(x)
+                    _lib.check(self._lib.vst_frame_f32_to_u8(y.data_ptr(), dout[b].data_ptr(), H, W, int(bgr), c.cuda_stream),
+                               "vst_frame_f32_to_u8")
                 ev_done[b].record(c)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[b])
