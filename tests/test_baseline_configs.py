@@ -281,14 +281,19 @@ def test_f16x2_range_guard_and_small_activations(dev):
         z = net(x.to(dev) * 100)
         scale = float(z_ref.abs().max())
         assert 50 < scale < 1000
-        assert maxdiff(z, z_ref) <= 1e-4 * scale
+        assert maxdiff(z, z_ref) <= 5e-4 * scale        # relative level of the unit-scale latent bar (Z_TOL 1e-3 at |z| ~ 2)
         assert net.check_status() is False and net.precision == "f16x2"
-        # (b) inputs x 1e-3
-        z_ref = O.revnet_forward(sd, x * 1e-3)
-        z = net(x.to(dev) * 1e-3)
-        assert maxdiff(z, z_ref) <= 2e-7
-        xr = net.inverse(z)
-        assert maxdiff(xr, x * 1e-3) <= 2e-7
+        # (b) inputs x 1e-3 on a bias-free net (every activation scales with the input: |x| down to ~1e-6)
+        net0 = build_net("photo", 0)
+        sd0 = cpu_state_dict(net0)
+        net0 = net0.to(dev)
+        z_ref = O.revnet_forward(sd0, x * 1e-3)
+        z = net0(x.to(dev) * 1e-3)
+        small = float(z_ref.abs().max())
+        assert small < 1e-2
+        print("tiny activations: |z| <= %.2e, err %.2e, round trip %.2e" % (small, maxdiff(z, z_ref), maxdiff(net0.inverse(z), x * 1e-3)))
+        assert maxdiff(z, z_ref) <= 5e-4 * small
+        assert maxdiff(net0.inverse(z), x * 1e-3) <= 1e-8          # fp32 noise at this scale is 1e-3 * 4e-7
         # (c) beyond the range
         net.range_check = "strict"
         z_ref = O.revnet_forward(sd, x * 5000)

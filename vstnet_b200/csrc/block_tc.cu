@@ -622,6 +622,8 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         const int xb0 = sg.x0 - 3 + m;                                       // image column of this thread in block 0
         const bool min_ok = (m >= 3) && (m < 3 + Cfg::XO);
         const size_t plane = (size_t)Hp * Wp;
+        const bool has_res = a.res != nullptr;                             // null: the coupling operand is zero (out = +/- F(x))
+        const bool res_ok = min_ok && has_res;
         const float4* resp = reinterpret_cast<const float4*>(a.res) + (size_t)(half * (CPT / 4)) * plane + (xb0 + 1);
         float4* outp = reinterpret_cast<float4*>(a.out) + (size_t)(half * (CPT / 4)) * plane;
         const float sgn = a.sub ? -1.f : 1.f;
@@ -637,13 +639,13 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         float4 rs[CH / 4], rn[CH / 4];                                       // coupling operand: current / next item
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j)
-            rs[j] = (min_ok && xb0 < W) ? resp[(size_t)j * plane + (size_t)(sg.ya + 1) * Wp] : make_float4(0.f, 0.f, 0.f, 0.f);
+            rs[j] = (res_ok && xb0 < W) ? resp[(size_t)j * plane + (size_t)(sg.ya + 1) * Wp] : make_float4(0.f, 0.f, 0.f, 0.f);
         BTC_ACC_BEGIN();
 #pragma unroll 1
         for (int y = sg.ya; y < sg.yb; ++y) {
             const int ly = y - sg.ya, sa = ly & (NA3 - 1);
             if (tid == 0) BTC_TRACE(4, 4 * ly);
-            if (tid < G && y + BTC_PREFETCH_ROWS < sg.yb)
+            if (has_res && tid < G && y + BTC_PREFETCH_ROWS < sg.yb)
                 l2_prefetch(reinterpret_cast<const float4*>(a.res) + (size_t)tid * plane + (size_t)(y + 1 + BTC_PREFETCH_ROWS) * Wp + sg.x0 + 1,
                             (uint32_t)(max(min(NB * Cfg::XO, W - sg.x0), 1) * 16));
             const size_t rowoff = (size_t)(y + 1) * Wp;
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                     {   // next item: block blk+1 of this row, or block 0 of the next row
                         const int nblk = (blk + 1 < NB) ? blk + 1 : 0;
                         const int ny = (blk + 1 < NB) ? y : y + 1;
-                        const bool nin = min_ok && (xb0 + nblk * Cfg::XO < W) && (ny < sg.yb);
+                        const bool nin = res_ok && (xb0 + nblk * Cfg::XO < W) && (ny < sg.yb);
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j)
                             rn[j] = nin ? resp[(size_t)j * plane + (size_t)(ny + 1) * Wp + nblk * Cfg::XO] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -726,7 +728,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                 const int x = xb0;
                 const bool xin = min_ok && (x < W);
 #pragma unroll
-                for (int j = 0; j < CH / 4; ++j) rs[j] = xin ? resp[(size_t)j * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < CH / 4; ++j) rs[j] = (xin && has_res) ? resp[(size_t)j * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
                 BTC_WAIT(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
                 tc_fence_after();
                 if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
@@ -759,7 +761,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                     if (c0 + CH < CPT) {        // next cout chunk of this row
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j)
-                            rn[j] = xin ? resp[(size_t)((c0 + CH) / 4 + j) * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            rn[j] = (xin && has_res) ? resp[(size_t)((c0 + CH) / 4 + j) * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     float el[CH], er[CH], bb[CH];
 #pragma unroll
@@ -834,7 +836,7 @@ static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
     a.trace_cta = std::min(a.n_strips * nseg - 1, a.n_strips * (nseg / 2) + a.n_strips / 2);
     const double px = (double)a.H * a.W;
     ProfScope prof(st, C == 16 ? "rev_block_tc 16>4>4>16" : "rev_block_tc 64>16>16>64",
-                   2.0 * 9 * (2.0 * C * Cfg::M + Cfg::M * Cfg::M) * px, 3.0 * 4.0 * C * px);
+                   2.0 * 9 * (2.0 * C * Cfg::M + Cfg::M * Cfg::M) * px, (a.res ? 3.0 : 2.0) * 4.0 * C * px);
     VST_CUDA_OK(launch_pdl(kern, a.n_strips * nseg, Cfg::THREADS, Cfg::SMEM, st, a));
     return check_launch("rev_block_tc");
 }

@@ -605,11 +605,18 @@ __global__ void __launch_bounds__(256) apply_kernel(const float* __restrict__ fe
         // ---- stage x (raw); 16-byte loads when the rows are 16-byte aligned and the tile is full
         const bool vec = ((n & 3) == 0) && npx == PX && ((((uintptr_t)feat | (uintptr_t)out) & 15) == 0);
         if (vec) {
-            for (int i = tid; i < CP * (PX / 4); i += 256) {
-                int k = i / (PX / 4), p4 = i - k * (PX / 4);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < C) v = __ldg(reinterpret_cast<const float4*>(feat + (size_t)k * n + p0) + p4);
-                reinterpret_cast<float4*>(xs + k * PX)[p4] = v;
+            // all loads of the tile are issued before the first shared-memory store (memory-level parallelism)
+            constexpr int NIT = CP * (PX / 4) / 256;
+            float4 v[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = it * 256 + tid, k = i / (PX / 4), p4 = i - k * (PX / 4);
+                v[it] = (k < C) ? __ldg(reinterpret_cast<const float4*>(feat + (size_t)k * n + p0) + p4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = it * 256 + tid, k = i / (PX / 4), p4 = i - k * (PX / 4);
+                reinterpret_cast<float4*>(xs + k * PX)[p4] = v[it];
             }
         } else {
             for (int i = tid; i < CP * PX; i += 256) {
@@ -743,15 +750,24 @@ __global__ void __launch_bounds__(256) apply_state_kernel(float* __restrict__ x1
         const int g0 = j * G;                                           // first state group of this sub-position
         float4* base = reinterpret_cast<float4*>(g0 < gph ? x1 : x2) + (size_t)(g0 < gph ? g0 : g0 - gph) * plane;
         __syncthreads();   // previous tile's smem fully consumed (and Tt staged)
-        for (int i = tid; i < G * PX; i += 256) {
-            const int g = i / PX, px = i - g * PX;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (px < npx) {
-                const int p = p0 + px, y = p / w, x = p - y * w;
-                v = base[(size_t)g * plane + (size_t)(y + 1) * Wp + x + 1];
+        {
+            // item (it, tid): group g = (it * 256 + tid) / PX, pixel px = tid % PX — the pixel is fixed per thread, so
+            // one division per tile; ALL loads are issued before the first shared-memory store (a load followed by its
+            // dependent store serialises one DRAM latency per item)
+            constexpr int NIT = G * PX / 256;
+            const int px = tid % PX, gq = tid / PX;
+            const int p = p0 + px, y = p / w, x = p - y * w;
+            const float4* src = base + (size_t)(y + 1) * Wp + x + 1;
+            float4 v[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; ++it)
+                v[it] = (px < npx) ? src[(size_t)(it * (256 / PX) + gq) * plane] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int g = it * (256 / PX) + gq;
+                xs[(4 * g + 0) * PX + px] = v[it].x; xs[(4 * g + 1) * PX + px] = v[it].y;
+                xs[(4 * g + 2) * PX + px] = v[it].z; xs[(4 * g + 3) * PX + px] = v[it].w;
             }
-            xs[(4 * g + 0) * PX + px] = v.x; xs[(4 * g + 1) * PX + px] = v.y;
-            xs[(4 * g + 2) * PX + px] = v.z; xs[(4 * g + 3) * PX + px] = v.w;
         }
         __syncthreads();
         float acc[8][4];

@@ -22,8 +22,10 @@
 //   * converters (8 warps): RAW -> subtract the pivot (fused mean subtraction; the exact mean correction is applied
 //     in the factor kernel from `sum`), split x = hi + lo (tf32 + remainder), transpose P4 units if needed, store both
 //     terms in the no-swizzle K-major canonical layout [k-chunk][row][4 floats] (row pitch padded: conflict-free).
-//   * UMMA issuer (1 thread): per stage 4 k-steps x 3 terms (hi.hi + hi.lo + lo.hi: fp32-equivalent products),
-//     kind::tf32, fp32 accumulators in TMEM, two accumulator buffers.
+//   * UMMA issuer (1 thread): per stage 4 k-steps x 2 UMMAs, kind::tf32, fp32 accumulators in TMEM, two buffers:
+//     D = H H^T + H (2L)^T.  The consumer (factor kernel) averages the two triangles of the accumulated matrix, and
+//     (D + D^T) / 2 = H H^T + H L^T + L H^T — the fp32-equivalent three-term product — so the third UMMA of the
+//     symmetric pair is never issued (a UMMA is bound by fetching its operands from shared memory: -1/3 of that traffic).
 //   * drain warps (4): every FL stages (split-K) pull the finished buffer out of TMEM and fold it into fp64
 //     (registers for C <= 64, global atomics for C = 128); at the end one fp64 atomicAdd per entry and CTA.
 #include <cuda.h>
@@ -175,7 +177,7 @@ gram_tc_kernel(GramTcArgs a, const __grid_constant__ CUtensorMap tm0, const __gr
                     const float4 h = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
                     const int dst = j * ROWP + seg * CP + c;
                     hi[dst] = h;
-                    lo[dst] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    lo[dst] = make_float4(2.f * (v.x - h.x), 2.f * (v.y - h.y), 2.f * (v.z - h.z), 2.f * (v.w - h.w));
                 }
             } else {
                 const int g = tid >> 3, j4 = tid & 7;
@@ -195,7 +197,7 @@ gram_tc_kernel(GramTcArgs a, const __grid_constant__ CUtensorMap tm0, const __gr
                     const float4 h = make_float4(tf32_round(v[0]), tf32_round(v[1]), tf32_round(v[2]), tf32_round(v[3]));
                     const int dst = j4 * ROWP + crow[e];
                     hi[dst] = h;
-                    lo[dst] = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
+                    lo[dst] = make_float4(2.f * (v[0] - h.x), 2.f * (v[1] - h.y), 2.f * (v[2] - h.z), 2.f * (v[3] - h.w));
                 }
             }
             fence_proxy_async();
@@ -243,8 +245,7 @@ gram_tc_kernel(GramTcArgs a, const __grid_constant__ CUtensorMap tm0, const __gr
                 for (int ks = 0; ks < KT / 8; ++ks) {
                     const uint64_t dh = make_desc(Hi + ks * 2 * LBO, LBO, SBO), dl = make_desc(Lo + ks * 2 * LBO, LBO, SBO);
                     umma_tf32(d, dh, dh, IDESC, (st % FL != 0 || ks > 0) ? 1u : 0u);
-                    umma_tf32(d, dh, dl, IDESC, 1u);
-                    umma_tf32(d, dl, dh, IDESC, 1u);
+                    umma_tf32(d, dh, dl, IDESC, 1u);       // H (2L)^T: with the symmetrisation below = H L^T + L H^T
                 }
                 umma_commit(&op_empty[s]);
                 if (st % FL == FL - 1 || st == n_stages - 1) umma_commit(&acc_full[b]);

@@ -195,9 +195,12 @@ int launch_factor(int mode, const void* content_stats, const void* const* style_
 size_t cwct_stats_bytes(int C, int n_labels);
 
 // layout / rearrangement kernels, layout.cu  (all tensors P4 unless stated)
-int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, cudaStream_t st);   // NCHW -> P4
+// NCHW -> P4; `add` (optional): a tiny P4 tensor [C0/4][add_h+2][add_w+2][4] whose centre pixel is added to every pixel
+int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, const float* add,
+                          int add_h, int add_w, cudaStream_t st);
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st);           // P4 -> NCHW
-int launch_image_u8_to_state(const uint8_t* hwc, float* s0, int C0, int H, int W, int bgr, int* status_clear, cudaStream_t st);
+int launch_image_u8_to_state(const uint8_t* hwc, float* s0, int C0, int H, int W, int bgr, int* status_clear,
+                             const float* add, int add_h, int add_w, cudaStream_t st);
 int launch_state_to_image_u8(const float* s0, uint8_t* hwc, int H, int W, int bgr, cudaStream_t st);
 int launch_space_to_depth(const float* in, float* out, int C, int Hin, int Win, cudaStream_t st);
 int launch_p4_replicate_topleft(float* t, int C, int H, int W, cudaStream_t st);

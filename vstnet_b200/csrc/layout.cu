@@ -12,18 +12,25 @@ static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 
 // injective_pad.forward + split (RevResNet.py:24-28, :8-12): x NCHW [Cimg][H][W] -> s0 P4 with C0
 // channels, channels >= Cimg zero.        injective_pad.inverse (:30-31): first Cimg channels of s0.
 // ------------------------------------------------------------------------------------------
+// `add` (optional): per-channel constant added to every pixel — F(0) of the first block when that block is folded
+// into this kernel (revnet.cu, fold_first_block): float4 per group, read from pixel (add_off) of a tiny P4 tensor.
+__device__ __forceinline__ float4 state_add_const(const float4* add, size_t add_plane, size_t add_off, int g) {
+    return add ? __ldg(add + (size_t)g * add_plane + add_off) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 __global__ void image_to_state_kernel(const float* __restrict__ x, float4* __restrict__ s0, int Cimg, int G, int H,
-                                      int W, int* __restrict__ status_clear) {
+                                      int W, int* __restrict__ status_clear, const float4* __restrict__ add,
+                                      size_t add_plane, size_t add_off) {
     if (status_clear && blockIdx.x == 0 && threadIdx.x == 0) *status_clear = 0;     // first kernel of an encode
     const size_t n = (size_t)H * W, total = (size_t)G * n;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int g = (int)(i / n);
         const size_t p = i - (size_t)g * n;
         const int y = (int)(p / W), xx = (int)(p - (size_t)y * W);
+        const float4 c = state_add_const(add, add_plane, add_off, g);
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = (4 * g + e < Cimg) ? __ldg(x + (size_t)(4 * g + e) * n + p) : 0.f;
-        p4_store(s0 + (size_t)g * p4_plane_px(H, W), H, W, y, xx, make_float4(v[0], v[1], v[2], v[3]));
+        p4_store(s0 + (size_t)g * p4_plane_px(H, W), H, W, y, xx, make_float4(v[0] + c.x, v[1] + c.y, v[2] + c.z, v[3] + c.w));
     }
 }
 __global__ void state_to_image_kernel(const float4* __restrict__ s0, float* __restrict__ x, int Cimg, int H, int W) {
@@ -44,7 +51,8 @@ __global__ void state_to_image_kernel(const float4* __restrict__ s0, float* __re
 // mul(255).clamp(0,255).byte() truncation of video_transfer.py:188, :211-214 folded into the first / last kernel of the
 // pass (bit-identical to vst_frame_u8_to_f32 / vst_frame_f32_to_u8 around the fp32 kernels).
 __global__ void image_u8_to_state_kernel(const uint8_t* __restrict__ hwc, float4* __restrict__ s0, int G, int H, int W, int bgr,
-                                         int* __restrict__ status_clear) {
+                                         int* __restrict__ status_clear, const float4* __restrict__ add, size_t add_plane,
+                                         size_t add_off) {
     if (status_clear && blockIdx.x == 0 && threadIdx.x == 0) *status_clear = 0;
     const size_t n = (size_t)H * W, total = (size_t)G * n;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -57,6 +65,8 @@ __global__ void image_u8_to_state_kernel(const uint8_t* __restrict__ hwc, float4
             const float r = (float)px[bgr ? 2 : 0] / 255.f, gg = (float)px[1] / 255.f, b = (float)px[bgr ? 0 : 2] / 255.f;
             v = make_float4(r, gg, b, 0.f);
         }
+        const float4 c = state_add_const(add, add_plane, add_off, g);
+        v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
         p4_store(s0 + (size_t)g * p4_plane_px(H, W), H, W, y, xx, v);
     }
 }
@@ -73,10 +83,13 @@ __global__ void state_to_image_u8_kernel(const float4* __restrict__ s0, uint8_t*
         }
     }
 }
-int launch_image_u8_to_state(const uint8_t* hwc, float* s0, int C0, int H, int W, int bgr, int* status_clear, cudaStream_t st) {
+int launch_image_u8_to_state(const uint8_t* hwc, float* s0, int C0, int H, int W, int bgr, int* status_clear,
+                             const float* add, int add_h, int add_w, cudaStream_t st) {
     const size_t total = (size_t)(C0 / 4) * H * W;
     ProfScope prof(st, "image_u8_to_state", 0.0, 3.0 * H * W + 16.0 * total);
-    image_u8_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(hwc, reinterpret_cast<float4*>(s0), C0 / 4, H, W, bgr, status_clear);
+    image_u8_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(hwc, reinterpret_cast<float4*>(s0), C0 / 4, H, W, bgr, status_clear,
+                                                            reinterpret_cast<const float4*>(add), p4_plane_px(add_h, add_w),
+                                                            (size_t)(add_h / 2 + 1) * (add_w + 2) + add_w / 2 + 1);
     return check_launch("image_u8_to_state");
 }
 int launch_state_to_image_u8(const float* s0, uint8_t* hwc, int H, int W, int bgr, cudaStream_t st) {
@@ -86,10 +99,13 @@ int launch_state_to_image_u8(const float* s0, uint8_t* hwc, int H, int W, int bg
     return check_launch("state_to_image_u8");
 }
 
-int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, cudaStream_t st) {
+int launch_image_to_state(const float* x, float* s0, int Cimg, int C0, int H, int W, int* status_clear, const float* add,
+                          int add_h, int add_w, cudaStream_t st) {
     const size_t total = (size_t)(C0 / 4) * H * W;
     ProfScope prof(st, "image_to_state", 0.0, 4.0 * Cimg * H * W + 16.0 * total);
-    image_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(x, reinterpret_cast<float4*>(s0), Cimg, C0 / 4, H, W, status_clear);
+    image_to_state_kernel<<<ew_grid(total), 256, 0, st>>>(x, reinterpret_cast<float4*>(s0), Cimg, C0 / 4, H, W, status_clear,
+                                                         reinterpret_cast<const float4*>(add), p4_plane_px(add_h, add_w),
+                                                         (size_t)(add_h / 2 + 1) * (add_w + 2) + add_w / 2 + 1);
     return check_launch("image_to_state");
 }
 int launch_state_to_image(const float* s0, float* x, int Cimg, int H, int W, cudaStream_t st) {

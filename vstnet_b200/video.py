@@ -186,33 +186,67 @@ class VideoStylizer:
 
     @torch.no_grad()
     def stylize_frames(self, frames, content_segs=None):
-        """Throughput path for a sequence of device frames (fp32 CUDA [1,3,H,W]): yields the stylized frames in
-        order, ``n_streams - 1`` frames behind the input.  Frame i runs on compute stream ``i % n_streams``; every
-        yielded tensor is ready on (and safe to use from) the caller's current stream."""
+        """Throughput path for a sequence of device frames (fp32 CUDA [1,3,H,W], or uint8 CUDA [H,W,3] on the fused
+        path): yields the stylized frames in order, ``n_streams - 1`` frames behind the input.  Frame i runs on compute
+        stream ``i % n_streams``; every yielded tensor is ready on (and safe to use from) the caller's current stream.
+        On the fused path the outputs live in a ring of ``2 n_streams + 2`` reused buffers (no allocator traffic in the
+        steady state): a yielded tensor stays valid until ``n_streams + 2`` more frames have been yielded — clone it
+        if it must live longer."""
         dev = next(self.net.parameters()).device
         cur = torch.cuda.current_stream(dev)
         cs = self._compute_streams(dev)
         n = len(cs)
         inflight = []                                   # (output, done event) in frame order
+        reuse, yielded = [], 0                          # ring slot per frame (fused path), frames handed out so far
         for i, f in enumerate(frames):
             s = cs[i % n]
             ev_in = torch.cuda.Event()                  # the frame may be produced lazily on the caller's stream (a
             ev_in.record(cur)                           # generator running device work): order it, and everything
             s.wait_event(ev_in)                         # enqueued before, ahead of its compute stream
             f.record_stream(s)
+            seg = None if content_segs is None else content_segs[i]
             with torch.cuda.stream(s):
-                y = self.stylize(f, None if content_segs is None else content_segs[i])
+                if self._fused_ok(f, seg):
+                    ring = self._out_ring(f, 2 * n + 2)
+                    slot = ring[i % len(ring)]
+                    s.wait_event(slot[1])                # the consumer's use of this buffer (recorded at yield time) is over
+                    a = 0.0 if self.alpha_c is None else float(self.alpha_c)
+                    y = self.net.stylize_frame(f, self.style_pre["stats"][0], a, self.cwct.eps, self.cwct.use_double, out=slot[0])
+                    reuse.append(slot)
+                else:
+                    y = self.stylize(f, seg)
+                    y.record_stream(cur)
+                    reuse.append(None)
                 ev = torch.cuda.Event()
                 ev.record(s)
-            y.record_stream(cur)
             inflight.append((y, ev))
             if len(inflight) >= n:
                 y0, e0 = inflight.pop(0)
                 cur.wait_event(e0)
+                self._mark_consumed(reuse, yielded, cur)
+                yielded += 1
                 yield y0
         for y0, e0 in inflight:
             cur.wait_event(e0)
+            self._mark_consumed(reuse, yielded, cur)
+            yielded += 1
             yield y0
+
+    @staticmethod
+    def _mark_consumed(reuse, k, cur):
+        """Frame k is being handed to the consumer: everything the consumer enqueued on `cur` for the frames yielded
+        before it is recorded into their ring slots, so that the slot's next producer waits for it."""
+        for j in (k - 1,):
+            if j >= 0 and reuse[j] is not None:
+                reuse[j][1].record(cur)
+
+    def _out_ring(self, like, depth):
+        k = ("outring", str(like.device), tuple(like.shape), like.dtype)
+        ring = self._pin.get(k)
+        if ring is None or len(ring) != depth:
+            ring = [(torch.empty_like(like), torch.cuda.Event()) for _ in range(depth)]
+            self._pin[k] = ring
+        return ring
 
     def _compute_streams(self, dev):
         k = ("compute", str(dev))
