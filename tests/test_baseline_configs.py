@@ -400,7 +400,8 @@ def test_fused_frame_path_equals_unfused(dev, mode, h, w, alpha):
     vs.fused = True
     u8 = (frame[0].permute(1, 2, 0) * 255).round().clamp(0, 255).byte().contiguous()
     o = net.stylize_frame(u8, vs.style_pre["stats"][0], 0.0 if alpha is None else alpha, bgr=True)
-    f = (u8.flip(-1).permute(2, 0, 1)[None].float() / 255).contiguous()
+    # byte / 255 on the CPU: a true division, as ToTensor does (torch's CUDA division by a scalar multiplies by 1/255)
+    f = (u8.cpu().flip(-1).permute(2, 0, 1)[None].float() / 255).contiguous().to(dev)
     yf = net.stylize_frame(f, vs.style_pre["stats"][0], 0.0 if alpha is None else alpha)
     want = yf[0].mul(255).clamp(0, 255).byte().permute(1, 2, 0).flip(-1)
     assert torch.equal(o, want)

@@ -231,17 +231,17 @@ class RevResNet(nn.Module):
 
     def _poll_range(self, block=False):
         keep, hit = [], False
-        for ev, host in self._range_pending:
+        for ev, host, fused in self._range_pending:
             if block:
                 ev.synchronize()
             if ev.query():
                 hit = hit or bool(int(host[0]) & 1)
-                if int(host[1]) < 0:             # fused frame path: the cWCT factorisation of that frame failed
+                if fused and int(host[1]) < 0:   # fused frame path: the cWCT factorisation of that frame failed
                     import warnings
                     warnings.warn("vstnet_b200: a Cholesky factorisation did not succeed within 64 jitter retries; that "
                                   "frame was returned unstylized", RuntimeWarning)
             else:
-                keep.append((ev, host))
+                keep.append((ev, host, fused))
         self._range_pending = keep
         return hit
 
@@ -283,7 +283,7 @@ class RevResNet(nn.Module):
                     return
                 if len(self._range_pending) >= 16:
                     self._range_pending.pop(0)
-                self._range_pending.append((ev, host))
+                self._range_pending.append((ev, host, call is not None))
                 return
 
     # ------------------------------------------------------------------ fused frame path (video)

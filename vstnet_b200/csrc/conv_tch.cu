@@ -16,22 +16,31 @@
 #include <stdlib.h>
 #include "kernels.cuh"
 #include <cuda_fp16.h>
-#include "tc_ptx.cuh"
+#include "tma_map.cuh"
 
 namespace vst {
 
+// Tile geometry (round 2): the 128 rows of a UMMA are FOUR IMAGE ROWS x 32 staged pixels (30 outputs + 2 halo pixels),
+// stacked vertically, instead of four 32-pixel windows of ONE image row.  Operand rows live as [k-half][image row][32 px]
+// [16 B] (row pitch 512 B), so the rows y..y+3 of a block are 128 consecutive "pixels" and tap ky is a start-address
+// shift of 512 B; the kx fold of the epilogue still never leaves a warp's 32 TMEM lanes (warp q = image row q of the
+// block).  A tile of R blocks is 4R rows x 30 pixels and stages (4R + 2) x 32 pixels: 1.33x its outputs (R = 2) instead
+// of 2.03x for two full-width rows — the L2 -> SM operand traffic per output pixel and 16-channel chunk drops from
+// 207 B to 158 B (activations 130 -> 85 B, weights 77 B), which is what bounded the 256 -> 64 conv.
+// The RAW tile of a chunk (4 groups x (4R + 2) rows x 32 pixels) arrives as ONE tensor-map TMA copy (3-D box).
 template <int NC, int R, int TERMS>
 struct TchCfg {
     static constexpr int NP = 3 * NC;               // UMMA N: (kx, cout)
     static constexpr int TA = TERMS >= 2 ? 2 : 1;   // activation terms (hi [, lo])
     static constexpr int TW = TERMS >= 3 ? 2 : 1;   // weight terms (hi [, lo])
-    static constexpr int PW = 128;                  // staged pixels per row = UMMA M
-    static constexpr int XS = 120;                  // outputs per tile row: four 32-row windows of 30 outputs + 2 halo pixels
-    static constexpr int ROWS = R + 2;
-    static constexpr int ROW_BYTES = PW * 16;       // one row of one 8-channel fp16 k-half (operand layout)
-    static constexpr int RAW_PW = 122;              // raw pixels staged per row: the four windows cover pixels 0..121
-    static constexpr int RAW_ROW_BYTES = RAW_PW * 16;               // one row of one 4-channel fp32 group
-    static constexpr int RAW_BYTES = 4 * ROWS * RAW_ROW_BYTES;      // 16 channels fp32
+    static constexpr int PW = 128;                  // UMMA M: 4 image rows x WIN staged pixels
+    static constexpr int WIN = 32;                  // staged pixels per image row
+    static constexpr int XS = 30;                   // outputs per tile row
+    static constexpr int TR = 4 * R;                // output rows per tile
+    static constexpr int ROWS = TR + 2;             // staged image rows
+    static constexpr int ROW_BYTES = WIN * 16;      // one image row of one 8-channel fp16 k-half (operand layout)
+    static constexpr int RAW_ROW_BYTES = WIN * 16;                  // one image row of one 4-channel fp32 group
+    static constexpr int RAW_BYTES = 4 * ROWS * RAW_ROW_BYTES;      // 16 channels fp32: [group][row][pixel][4 floats]
     static constexpr int A_TERM_BYTES = 2 * ROWS * ROW_BYTES;       // 16 channels fp16: [k-half][row][pixel][8 halfs]
     static constexpr int A_BYTES = TA * A_TERM_BYTES;
     static constexpr int B_TERM_BYTES = 3 * 2 * NP * 16;            // [ky][k-half][n'][8 halfs]
@@ -41,7 +50,7 @@ struct TchCfg {
     static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
     static constexpr int AUX_BYTES = 2048;                          // barriers (1 KB) + bias (1 KB)
-    static constexpr int NO = 2;                                    // operand ring depth
+    static constexpr int NO = 3;                                    // operand ring depth
     static constexpr int NR_FIT = (226 * 1024 - AUX_BYTES - NO * OP_BYTES) / RAW_BYTES;
     static constexpr int NR = NR_FIT > 4 ? 4 : NR_FIT;              // raw ring depth
     static constexpr size_t SMEM = (size_t)NR * RAW_BYTES + (size_t)NO * OP_BYTES + AUX_BYTES + 128;
@@ -141,9 +150,11 @@ constexpr int TCH_NCW = 8;         // converter warps: with 4 the fp32 -> fp16 h
 constexpr int TCH_THREADS = (8 + TCH_NCW + 3) * 32;   // 8 epilogue + converter warps, activation producer, UMMA issuer, weight producer
 
 template <int NC, int R, int TERMS, bool SPLIT>   // SPLIT: H8 split-half output (compile time: each variant keeps its own registers)
-__global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a, TchTiles tl) {
+__global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a, TchTiles tl,
+                                                                     const __grid_constant__ CUtensorMap tm_in) {
     using Cfg = TchCfg<NC, R, TERMS>;
-    constexpr int NR = Cfg::NR, NO = Cfg::NO, PW = Cfg::PW, ROWS = Cfg::ROWS, NP = Cfg::NP, NACC = Cfg::NACC, XS = Cfg::XS;
+    constexpr int NR = Cfg::NR, NO = Cfg::NO, WIN = Cfg::WIN, ROWS = Cfg::ROWS, NP = Cfg::NP, NACC = Cfg::NACC, XS = Cfg::XS;
+    constexpr int TR = Cfg::TR;
     pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* raw_base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -179,27 +190,20 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     if (warp == W_PROD) {
         // ================= activation producer (TMA): raw fp32 P4 rows of 16 channels -> RAW ring =================
         if (lane == 0) {
-            const int Hp = a.Hin + 2, Wp = a.Win + 2;
-            const float4* in4 = reinterpret_cast<const float4*>(a.in);
             uint32_t it = 0;
             for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
                 const int rest = t / tl.n_ct;
-                const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * R;
+                const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * TR;
                 for (int c = 0; c < n_chunks; ++c, ++it) {
                     const int s = it % NR;
                     mbar_wait(&raw_empty[s], ((it / NR) & 1) ^ 1);
                     TCH_TRACE(0, it);
                     uint8_t* A = raw_base + (size_t)s * Cfg::RAW_BYTES;
                     mbar_arrive_expect_tx(&raw_full[s], Cfg::RAW_BYTES);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-#pragma unroll
-                        for (int row = 0; row < ROWS; ++row) {
-                            const int py = min(y0 + row, Hp - 1);     // padded row of image row y0-1+row
-                            // tile pixel p <-> padded column xs + p (image x = xs - 1 + p)
-                            bulk_g2s(A + (g * ROWS + row) * Cfg::RAW_ROW_BYTES,
-                                     in4 + ((size_t)(4 * c + g) * Hp + py) * Wp + xs, Cfg::RAW_ROW_BYTES, &raw_full[s]);
-                        }
+                    // box {32 pixels x 4 floats, ROWS rows, 4 groups}: tile pixel p <-> padded column xs + p (image
+                    // x = xs - 1 + p), staged row r <-> padded row y0 + r (image row y0 - 1 + r); rows / columns
+                    // past the padded plane arrive as zeros and only feed outputs that are never stored
+                    tma_load_3d(A, &tm_in, xs * 4, y0, 4 * c, &raw_full[s]);
                 }
             }
         }
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
         if (lane == 0) {
             // kind::f16: D = F32 (bit 4), A = B = F16 (format 0), N at bit 17, M at bit 24
             constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
-            constexpr uint32_t A_LBO = ROWS * Cfg::ROW_BYTES, B_LBO = NP * 16, SBO = 128;
+            constexpr uint32_t A_LBO = ROWS * Cfg::ROW_BYTES, B_LBO = NP * 16, SBO = 128;     // A: 4 image rows = 128 contiguous operand rows
             uint32_t it = 0, tcount = 0;
             for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
                 const uint32_t b = tcount % NACC;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                         const uint64_t bh = make_desc(Baddr + ky * 2 * NP * 16, B_LBO, SBO);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const uint32_t aoff = (r + ky) * Cfg::ROW_BYTES;
+                            const uint32_t aoff = (4 * r + ky) * Cfg::ROW_BYTES;
                             const uint32_t d = acc + r * NP;
                             const uint32_t first = (c > 0 || ky > 0) ? 1u : 0u;
                             umma_f16(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
@@ -278,13 +282,10 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                 uint4* hi = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES);
                 uint4* lo = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES + Cfg::A_TERM_BYTES);
 #pragma unroll 4
-                for (int i = ctid; i < 2 * ROWS * PW; i += 32 * TCH_NCW) {
-                    const int kh = i / (ROWS * PW), rm = i - kh * (ROWS * PW);      // k-half, (row, operand row m)
-                    // operand row m = 32q + l of an image row holds staged pixel 30q + l: the kx fold of the epilogue
-                    // (m-1, m, m+1) then never leaves a warp's 32 TMEM lanes — no cross-warp exchange
-                    const int mm = rm & (PW - 1), rp = (rm >> 7) * Cfg::RAW_PW + 30 * (mm >> 5) + (mm & 31);   // PW = 128
-                    const float4 u = raw[(2 * kh) * (ROWS * Cfg::RAW_PW) + rp];
-                    const float4 v = raw[(2 * kh + 1) * (ROWS * Cfg::RAW_PW) + rp];
+                for (int i = ctid; i < 2 * ROWS * WIN; i += 32 * TCH_NCW) {
+                    const int kh = i / (ROWS * WIN), rp = i - kh * (ROWS * WIN);    // k-half, (image row, pixel): same index in RAW
+                    const float4 u = raw[(2 * kh) * (ROWS * WIN) + rp];
+                    const float4 v = raw[(2 * kh + 1) * (ROWS * WIN) + rp];
                     const float x[8] = {u.x * VST_HALF_SCALE, u.y * VST_HALF_SCALE, u.z * VST_HALF_SCALE, u.w * VST_HALF_SCALE,
                                         v.x * VST_HALF_SCALE, v.y * VST_HALF_SCALE, v.z * VST_HALF_SCALE, v.w * VST_HALF_SCALE};
                     uint32_t hw[4];
@@ -314,8 +315,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
         // lane l of warp (q, half) owns tile pixel m = 32q + l and the cout half `half`.
         constexpr int HC = NC / 2;                         // couts per thread
         constexpr int CH = HC >= 16 ? 16 : HC;             // couts per TMEM load
-        const int q = warp & 3, half = warp >> 2;
-        const int pm = q * 30 + lane;                      // staged pixel held by this thread's TMEM lane (window layout)
+        const int q = warp & 3, half = warp >> 2;          // q: image row of the block held by this warp's 32 TMEM lanes
         const float flo = (a.epi == EPI_RELU) ? 0.f : -INFINITY;
         const int H = a.Hout, W = a.Wout, Wp = W + 2;
         const size_t plane = p4_plane_px(H, W);
@@ -323,20 +323,21 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
         uint32_t hmax = 0u;                    // fp16 range guard of the H8 output (tc_ptx.cuh)
         for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
             const int ct = t % tl.n_ct, rest = t / tl.n_ct;
-            const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * R;
+            const int xs = (rest % tl.n_xt) * XS, y0 = (rest / tl.n_xt) * TR;
             const uint32_t b = tcount % NACC;
-            const int x = xs - 1 + pm;
-            const bool xin = (lane >= 1) && (lane <= 30) && (x < W);
-            const int rows = min(R, H - y0);
+            const int x = xs - 1 + lane;
+            const bool xok = (lane >= 1) && (lane <= 30) && (x < W);
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * Cfg::ACC_COLS + half * HC;
             mbar_wait(&acc_full[b], (tcount / NACC) & 1);
             tc_fence_after();
             if (tid == 0) TCH_TRACE(6, tcount);
             // out[m] = D[m-1][kx=0] + D[m][kx=1] + D[m+1][kx=2], all within the warp
-            const bool lf = xin && (x == 1), rt = xin && (x == W - 2);
+            const bool lf = xok && (x == 1), rt = xok && (x == W - 2);
 #pragma unroll 1
-            for (int r = 0; r < rows; ++r) {
-                const int y = y0 + r;
+            for (int r = 0; r < R; ++r) {
+                const int y = y0 + 4 * r + q;
+                if (y0 + 4 * r >= H) break;                       // (warp-uniform) no rows of this block inside the image
+                const bool xin = xok && (y < H);
                 const bool up = (y == 1), dn = (y == H - 2);
 #pragma unroll 1
                 for (int c0 = 0; c0 < HC; c0 += CH) {
@@ -453,15 +454,23 @@ static int launch_tch_cfg2(const ConvArgs& a, cudaStream_t st) {
     auto kern = conv3x3_tch_kernel<NC, R, TERMS, SPLIT>;
     VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     TchTiles tl;
-    tl.n_xt = cdiv(a.Wout, Cfg::XS); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / NC;
+    tl.n_xt = cdiv(a.Wout, Cfg::XS); tl.n_yt = cdiv(a.Hout, Cfg::TR); tl.n_ct = a.Cout / NC;
     tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;
     tl.trace = tc_trace_buffer(a.Cin, a.Cout, st);
     const int grid = std::min(tl.n_tiles, num_sms());
+    // the input as a rank-3 fp32 tensor {(W+2) * 4 floats, H+2 rows, Cin/4 groups}; one box = the RAW tile of a chunk
+    CUtensorMap tm;
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)(a.Win + 2) * 4, (cuuint64_t)(a.Hin + 2), (cuuint64_t)(a.Cin / 4)};
+        const cuuint64_t strides[2] = {(cuuint64_t)(a.Win + 2) * 16, (cuuint64_t)(a.Hin + 2) * (a.Win + 2) * 16};
+        const cuuint32_t box[3] = {(cuuint32_t)Cfg::WIN * 4, (cuuint32_t)Cfg::ROWS, 4};
+        if (make_tensor_map_f32(&tm, 3, a.in, dims, strides, box)) return 2;
+    }
     char cls[40];
     snprintf(cls, sizeof(cls), "conv3x3_tch%d %d>%d", TERMS, a.Cin, a.Cout);
     const double px = (double)a.Hout * a.Wout;
     ProfScope prof(st, cls, 2.0 * 9 * a.Cin * a.Cout * px, 4.0 * ((double)a.Cin * a.Hin * a.Win + a.Cout * px));
-    VST_CUDA_OK(launch_pdl(kern, grid, TCH_THREADS, Cfg::SMEM, st, a, tl));
+    VST_CUDA_OK(launch_pdl(kern, grid, TCH_THREADS, Cfg::SMEM, st, a, tl, tm));
     return check_launch("conv3x3_tch");
 }
 

@@ -28,9 +28,8 @@
 //     symmetric pair is never issued (a UMMA is bound by fetching its operands from shared memory: -1/3 of that traffic).
 //   * drain warps (4): every FL stages (split-K) pull the finished buffer out of TMEM and fold it into fp64
 //     (registers for C <= 64, global atomics for C = 128); at the end one fp64 atomicAdd per entry and CTA.
-#include <cuda.h>
 #include "kernels.cuh"
-#include "tc_ptx.cuh"
+#include "tma_map.cuh"
 
 namespace vst {
 
@@ -61,17 +60,6 @@ struct GramTcArgs {
     int h, w, n_xb, n_jb, groups_per_half;
     int stages_per_cta, n_stages;
 };
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 template <int SEGS, int SRC>
 __global__ void __launch_bounds__(gtc::THREADS, 1)
@@ -317,11 +305,11 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
+int make_tensor_map_f32(CUtensorMap* tm, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                        const cuuint32_t* box) {
     EncodeTiledFn fn = encode_tiled_fn();
     VST_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint32_t es[3] = {1, 1, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -358,7 +346,7 @@ int launch_gram_tc(const float* feat, const float* pivot, double* count, double*
     const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)C};
     const cuuint64_t strides[1] = {(cuuint64_t)n * 4};
     const cuuint32_t box[2] = {(cuuint32_t)(segs * gtc::KT), (cuuint32_t)C};
-    if (make_map(&tm, 2, feat, dims, strides, box)) return 2;
+    if (make_tensor_map_f32(&tm, 2, feat, dims, strides, box)) return 2;
     if (segs == 4) return launch_gram_tc_cfg<4, gtc::SRC_NCHW>(a, tm, tm, st);
     if (segs == 2) return launch_gram_tc_cfg<2, gtc::SRC_NCHW>(a, tm, tm, st);
     return launch_gram_tc_cfg<1, gtc::SRC_NCHW>(a, tm, tm, st);
@@ -384,7 +372,7 @@ int launch_gram_tc_state(const float* x1, const float* x2, const float* pivot, d
     const cuuint64_t dims[3] = {(cuuint64_t)(w + 2) * 4, (cuuint64_t)(h + 2), (cuuint64_t)(Ch / 4)};
     const cuuint64_t strides[2] = {(cuuint64_t)(w + 2) * 16, (cuuint64_t)(h + 2) * (w + 2) * 16};
     const cuuint32_t box[3] = {(cuuint32_t)gtc::KT * 4, 1, 32};
-    if (make_map(&tm[0], 3, x1, dims, strides, box) || make_map(&tm[1], 3, x2, dims, strides, box)) return 2;
+    if (make_tensor_map_f32(&tm[0], 3, x1, dims, strides, box) || make_tensor_map_f32(&tm[1], 3, x2, dims, strides, box)) return 2;
     const int segs = 128 / C;
     if (segs == 4) return launch_gram_tc_cfg<4, gtc::SRC_STATE>(a, tm[0], tm[1], st);
     if (segs == 2) return launch_gram_tc_cfg<2, gtc::SRC_STATE>(a, tm[0], tm[1], st);
