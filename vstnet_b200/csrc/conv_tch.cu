@@ -484,6 +484,18 @@ int launch_conv3x3_tch(const ConvArgs& a, int terms, cudaStream_t st) {
     VST_REQUIRE(a.epi == EPI_RELU || a.epi == EPI_NONE, "conv3x3_tch has no coupling epilogue");
     VST_REQUIRE(a.Hin == a.Hout && a.Win == a.Wout && a.Hin >= 2 && a.Win >= 2, "conv3x3_tch is stride 1, H,W >= 2");
     if (a.Cout == 64) {
+        // Few input chunks (Cin <= 64: the 64 -> 64 convs): a tile's UMMA phase (4 chunks, ~5 k cycles) is as short as
+        // its epilogue (~5 k cycles, role traces), so the two must overlap — one 4-row block per tile (R = 1) leaves room
+        // for a double-buffered accumulator (2 x 192 TMEM columns).  Cin = 256 keeps two blocks per tile (R = 2, single
+        // accumulator): its 16-chunk UMMA phase dominates and the larger tile halves the weight traffic from L2.
+        // (Releasing the accumulator block by block before the store phase was measured: +7 % on the 256 -> 64 conv.)
+        static int r1 = -1;
+        if (r1 < 0) { const char* e = getenv("VST_TCH_R1"); r1 = e ? atoi(e) : 1; }
+        if (a.Cin <= 64 && r1) {
+            if (terms == 1) return launch_tch_cfg<64, 1, 1>(a, st);
+            if (terms == 2) return launch_tch_cfg<64, 1, 2>(a, st);
+            return launch_tch_cfg<64, 1, 3>(a, st);
+        }
         if (terms == 1) return launch_tch_cfg<64, 2, 1>(a, st);
         if (terms == 2) return launch_tch_cfg<64, 2, 2>(a, st);
         return launch_tch_cfg<64, 2, 3>(a, st);
