@@ -144,6 +144,12 @@ size_t vst_cwct_stats_bytes(int C, int n_labels);
 int vst_cwct_stats(const float* feat, int C, long long n, const uint8_t* labels, int n_labels,
                    void* stats, void* stream);
 
+/* The same for a feature map whose 2-D shape is known, feat [C, H*W], labels [H*W]: large per-label maps of the
+ * photorealistic latent (C = 32) then run on the tensor cores (strip-wise traversal, one masked-covariance pass per
+ * label present in a stage); everything else behaves as vst_cwct_stats. */
+int vst_cwct_stats2d(const float* feat, int C, int H, int W, const uint8_t* labels, int n_labels,
+                     void* stats, void* stream);
+
 /* Per label: covariance (n-1 divisor), Cholesky with the cumulative eps*I retry (cWCT.py:111-128),
  * triangular solve, T = (1-alpha_c) * (sum_k alpha_s[k] Ls_k) Lc^-1 + alpha_c I,
  * mu = mu_c,  beta = (1-alpha_c) sum_k alpha_s[k] mu_s,k + alpha_c mu_c   (out = T (x - mu) + beta).

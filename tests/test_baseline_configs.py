@@ -471,3 +471,34 @@ def test_labels_from_colors_on_device(dev, tmp_path):
     ref = O.cwct_transfer_seg(zc, zs, lab.cpu().numpy()[None], lab.cpu().numpy()[None])
     got = cWCT().transfer(zc.to(dev), zs.to(dev), lab[None], lab[None])
     assert maxdiff(got, ref) <= 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# per-label statistics on the tensor cores (gram_tc_masked_kernel: n >= 16384, C = 32)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w,kind", [(128, 192, "blocky"), (136, 260, "blocky"), (96, 256, "speckled"), (200, 132, "stripes")])
+def test_masked_transfer_tensor_core_stats_vs_oracle(dev, h, w, kind):
+    """Label maps of the size class that takes the tensor-core masked Gram: region-like maps (one label per stage, two
+    where regions meet), vertical stripes narrower than a stage (every stage mixed), per-pixel random labels (every
+    stage holds every label), widths that are not a multiple of the 128-pixel stage, an invalid and an absent label."""
+    from vstnet_b200 import _lib, cWCT
+    g = torch.Generator().manual_seed(h + w)
+    zc = torch.randn(1, 32, h, w, generator=g) * 0.5 + 0.1
+    zs = torch.randn(1, 32, h, w, generator=g) * 0.3 - 0.2
+    if kind == "blocky":
+        cm = bench.blocky_mask(h, w, 2, 4, [0, 1, 2, 3, 4, 5, 6, 7])
+        sm = bench.blocky_mask(h, w, 4, 2, [3, 1, 0, 2, 7, 6, 4, 4])            # label 5 absent from the style
+        cm[0, :3, :2] = 9                                                       # 6 pixels: invalid (too few)
+    elif kind == "stripes":
+        cm = (np.arange(w)[None, None, :] // 20 % 5).astype(np.uint8).repeat(h, 1)
+        sm = (np.arange(h)[None, :, None] // 16 % 5).astype(np.uint8).repeat(w, 2)
+    else:
+        cm = torch.randint(0, 4, (1, h, w), generator=g, dtype=torch.uint8).numpy()
+        sm = torch.randint(0, 4, (1, h, w), generator=g, dtype=torch.uint8).numpy()
+    ref = O.cwct_transfer_seg(zc, zs, cm, sm)
+    n0 = _lib.launch_count()
+    out = cWCT().transfer(zc.to(dev).clone(), zs.to(dev), torch.from_numpy(cm).to(dev), torch.from_numpy(sm).to(dev))
+    assert _lib.launch_count() - n0 >= 4
+    err = maxdiff(out, ref)
+    print("masked TC stats %s %dx%d: %.2e" % (kind, h, w, err))
+    assert err <= 1e-4

@@ -63,6 +63,7 @@ SIGNATURES = {
                                      C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vst_cwct_stats_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "vst_cwct_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "vst_cwct_stats2d": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vst_cwct_factor": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_float), C.c_int, C.c_float,
                                   C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -83,8 +83,13 @@ class cWCT(nn.Module):
         return None if self.last_status is None else self.last_status.cpu().tolist()
 
     # ------------------------------------------------------------------ low-level steps
-    def _stats(self, feat2d, C_, n, labels, L, stream):
+    def _stats(self, feat2d, C_, n, labels, L, stream, hw=None):
         buf = torch.empty(int(self._lib.vst_cwct_stats_bytes(C_, L)), dtype=torch.uint8, device=feat2d.device)
+        if labels is not None and hw is not None and hw[0] * hw[1] == n:
+            # the 2-D shape lets large per-label maps run on the tensor cores (strip-wise traversal)
+            _lib.check(self._lib.vst_cwct_stats2d(feat2d.data_ptr(), C_, int(hw[0]), int(hw[1]), labels.data_ptr(), L,
+                                                  buf.data_ptr(), stream), "vst_cwct_stats2d")
+            return buf
         _lib.check(self._lib.vst_cwct_stats(feat2d.data_ptr(), C_, n, labels.data_ptr() if labels is not None else None,
                                             L, buf.data_ptr(), stream), "vst_cwct_stats")
         return buf
@@ -312,7 +317,7 @@ class cWCT(nn.Module):
                 if n_labels is not None:                # a fixed number of label slots (multi-GPU: every rank
                     L = max(L, int(n_labels))           # knows the buffer size without communication)
             for i in range(B):
-                stats.append(self._stats(style[i], N, ns, masks[i][0] if smask is not None else None, L, st))
+                stats.append(self._stats(style[i], N, ns, masks[i][0] if smask is not None else None, L, st, (sH, sW)))
         return {"stats": stats, "L": L, "masked": smask is not None, "C": N}
 
     @torch.no_grad()
@@ -334,7 +339,7 @@ class cWCT(nn.Module):
             st = torch.cuda.current_stream(dev).cuda_stream
             for i in range(B):
                 cm = self._mask_to_device(cmask[i], n, dev, "cmask", (cH, cW))[0] if masked else None
-                cst = self._stats(content[i], N, n, cm, L, st)
+                cst = self._stats(content[i], N, n, cm, L, st, (cH, cW))
                 T, mu, beta, valid = self._factor(cst, [style_pre["stats"][i]], [1.0], 0.0 if masked else alpha_c, N, L,
                                                   masked, dev, st)
                 self._apply(content[i], out[i], N, n, cm, L, T, mu, beta, valid, st)
@@ -367,8 +372,8 @@ class cWCT(nn.Module):
                 # a device mask is never read back, label 255 is then an ordinary label).
                 if L > 255 and not (isinstance(cmask[i], torch.Tensor) and cmask[i].is_cuda):
                     raise IndexError("content label 255 is not supported (ref: cWCT.py:173 overflows uint8)")
-                cst = self._stats(content_feat[i], N, nc, cm, L, st)
-                sst = self._stats(style[i], N, ns, sm, L, st)
+                cst = self._stats(content_feat[i], N, nc, cm, L, st, (cH, cW))
+                sst = self._stats(style[i], N, ns, sm, L, st, (sH, sW))
                 T, mu, beta, valid = self._factor(cst, [sst], [1.0], 0.0, N, L, True, dev, st)
                 self._apply(content_feat[i], content_feat[i], N, nc, cm, L, T, mu, beta, valid, st)
         return content_feat

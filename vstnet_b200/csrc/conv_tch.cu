@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     constexpr int TR = Cfg::TR;
     pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* raw_base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t* raw_base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // by offset: keeps the __shared__ address space (LDS / STS)
     uint8_t* op_base = raw_base + (size_t)NR * Cfg::RAW_BYTES;
     uint64_t* bars = (uint64_t*)(op_base + (size_t)NO * Cfg::OP_BYTES);
     uint64_t* raw_full = bars;                  // [NR]    activation producer arrive.expect_tx + TMA bytes

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(TCX_THREADS, 1) conv3x3_tcx_kernel(ConvArgs a,
     using Cfg = TcxCfg<NC, R, TERMS>;
     constexpr int NS = Cfg::NS, PW = Cfg::PW, ROWS = Cfg::ROWS, NP = Cfg::NP, NACC = Cfg::NACC, XS = Cfg::XS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* stage_base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t* stage_base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // by offset: keeps the __shared__ address space (LDS / STS)
     uint64_t* bars = (uint64_t*)(stage_base + (size_t)NS * Cfg::STAGE_BYTES);
     uint64_t* loaded = bars;                    // [NS]    operand producer arrive.expect_tx + TMA bytes
     uint64_t* ready = bars + NS;                // [NS]    128 converter threads

@@ -181,6 +181,10 @@ int launch_pack_tch_s2_weights(const float* w, float* wp, int C, int Cout, cudaS
 bool gram_tc_eligible(int C, long long n);
 int launch_gram_tc(const float* feat, const float* pivot, double* count, double* sum, double* gram, int C, long long n,
                    cudaStream_t st);
+// per-label statistics on the tensor cores (label map [H*W] uint8, strip-major traversal), gram_tc.cu
+bool gram_tc_masked_eligible(int C, int H, int W);
+int launch_gram_tc_masked(const float* feat, const uint8_t* labels, const float* pivot, double* count, double* sum, double* gram,
+                          int C, int L, int H, int W, cudaStream_t st);
 // ... of the latent that the P4 half-states x1 | x2 (Ch channels each, h x w) spread to, without materialising it
 int launch_gram_tc_state(const float* x1, const float* x2, const float* pivot, double* count, double* sum, double* gram, int C,
                          int Ch, int h, int w, cudaStream_t st);
