@@ -35,7 +35,11 @@ namespace vst {
 // ------------------------------------------------------------------------------------------
 // configuration
 // ------------------------------------------------------------------------------------------
-template <int N, int R, int TERMS, bool HALF = false>
+// WST ("weights stationary", HALF only, Cin = 64): a persistent CTA always works on the same cout tile (the grid is a
+// multiple of the number of cout tiles), so all of its fp16 weights — 4 chunks x 36 KB for N = 128 — are fetched ONCE
+// and stay resident in shared memory; a pipeline stage then carries activations only.  The 64 -> 256 coupling conv was
+// bound by L2 -> SM traffic (69 KB per chunk and tile, more than half of it weights that every tile re-read).
+template <int N, int R, int TERMS, bool HALF = false, bool WST = false>
 struct TcCfg {
     static constexpr int KCH = HALF ? 16 : 8;       // input channels per pipeline stage (one UMMA K)
     static constexpr int TA = TERMS >= 2 ? 2 : 1;   // activation terms staged (hi [, lo])
@@ -47,13 +51,16 @@ struct TcCfg {
     static constexpr int A_BYTES = TA * A_TERM_BYTES;
     static constexpr int B_TERM_BYTES = 9 * 2 * N * 16;
     static constexpr int B_BYTES = TW * B_TERM_BYTES;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int WST_CHUNKS = 4;            // resident weight chunks (Cin = 64)
+    static constexpr int W_RES_BYTES = WST ? WST_CHUNKS * B_BYTES : 0;
+    static constexpr int STAGE_BYTES = WST ? A_BYTES : A_BYTES + B_BYTES;
     static constexpr int AUX_BYTES = 2048;          // barriers (1 KB) + bias (<= 256 floats)
-    static constexpr int NS_FIT = (226 * 1024 - AUX_BYTES) / STAGE_BYTES;
+    static constexpr int NS_FIT = (226 * 1024 - AUX_BYTES - W_RES_BYTES) / STAGE_BYTES;
     static constexpr int NS = NS_FIT > 4 ? 4 : NS_FIT;
     static constexpr int ACC_COLS = R * N;          // one accumulator buffer
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-    static constexpr size_t SMEM = (size_t)NS * STAGE_BYTES + AUX_BYTES + 128;
+    static constexpr size_t SMEM = (size_t)NS * STAGE_BYTES + W_RES_BYTES + AUX_BYTES + 128;
+    static_assert(!WST || HALF, "resident weights are for the fp16 operand path");
     static_assert(2 * ACC_COLS <= 512, "double-buffered accumulators exceed TMEM");
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA M=128 needs N % 16 == 0");
     static_assert(NS >= 2, "need at least a double-buffered operand pipeline");
@@ -116,19 +123,21 @@ __device__ __forceinline__ void umma_f16_tc(uint32_t d_tmem, uint64_t a_desc, ui
 
 // HALF = true: the input is an H8 split-half tensor (kernels.cuh): hi and lo rows arrive by TMA already in
 // the K-major fp16 operand layout, there is no converter stage, and the UMMAs are kind::f16 with K = 16.
-template <int N, int R, int TERMS, bool HALF, bool SQZ>
+template <int N, int R, int TERMS, bool HALF, bool SQZ, bool WST = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, TcTiles tl) {
-    using Cfg = TcCfg<N, R, TERMS, HALF>;
+    using Cfg = TcCfg<N, R, TERMS, HALF, WST>;
     constexpr int NS = Cfg::NS, PW = Cfg::PW, ROWS = Cfg::ROWS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* stage_base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // by offset: keeps the __shared__ address space (LDS / STS)
-    uint64_t* bars = (uint64_t*)(stage_base + (size_t)NS * Cfg::STAGE_BYTES);
+    uint8_t* wres = stage_base + (size_t)NS * Cfg::STAGE_BYTES;        // WST: [chunk][tap][k-half][n][8 halfs], resident
+    uint64_t* bars = (uint64_t*)(wres + Cfg::W_RES_BYTES);
     uint64_t* loaded = bars;                    // [NS]  operand producer arrive.expect_tx + TMA bytes
     uint64_t* ready = bars + NS;                // [NS]  128 converter threads
     uint64_t* empty = bars + 2 * NS;            // [NS]  tcgen05.commit
     uint64_t* acc_full = bars + 3 * NS;         // [2]   tcgen05.commit
     uint64_t* acc_empty = bars + 3 * NS + 2;    // [2]   256 epilogue threads
     uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NS + 4);
+    uint64_t* wbar = bars + 3 * NS + 5;         // WST: the resident weights have landed
     float* bias_s = (float*)((uint8_t*)bars + 1024);
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < a.Cout && i < 256; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
@@ -142,6 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&loaded[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
+        mbar_init(wbar, 1);
         fence_barrier_init();
     }
     if (warp == 13) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -161,6 +171,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
             const int Hp = a.Hin + 2, Wp = a.Win + 2;
             const float4* in4 = reinterpret_cast<const float4*>(a.in);
             uint32_t it = 0;
+            if (WST) {
+                // every tile of this CTA has cout tile blockIdx.x % n_ct (gridDim.x is a multiple of n_ct)
+                const float* wsrc = a.w + (size_t)(blockIdx.x % tl.n_ct) * n_chunks * (Cfg::B_BYTES / 4);
+                mbar_arrive_expect_tx(wbar, (uint32_t)(n_chunks * Cfg::B_BYTES));
+                for (int c = 0; c < n_chunks; ++c)
+                    bulk_g2s(wres + (size_t)c * Cfg::B_BYTES, wsrc + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, wbar);
+            }
             for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
                 const int ct = t % tl.n_ct, rest = t / tl.n_ct;
                 const int x0 = (rest % tl.n_xt) * 128, y0 = (rest / tl.n_xt) * R;
@@ -171,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                     TC_TRACE(0, it);
                     uint8_t* A = stage_base + (size_t)s * Cfg::STAGE_BYTES;
                     constexpr int NT = HALF ? Cfg::TA : 1;            // tensors to fetch: raw fp32 | hi, lo
-                    mbar_arrive_expect_tx(&loaded[s], NT * Cfg::A_TERM_BYTES + Cfg::B_BYTES);
+                    mbar_arrive_expect_tx(&loaded[s], NT * Cfg::A_TERM_BYTES + (WST ? 0 : Cfg::B_BYTES));
 #pragma unroll
                     for (int term = 0; term < NT; ++term) {
                         // H8: the lo planes follow the Cin/8 hi planes; both are addressed like P4 groups
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                                          src + ((size_t)(2 * c + g) * Hp + py) * Wp + x0, Cfg::ROW_BYTES, &loaded[s]);
                             }
                     }
-                    bulk_g2s(A + Cfg::A_BYTES, wsrc + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &loaded[s]);
+                    if (!WST) bulk_g2s(A + Cfg::A_BYTES, wsrc + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &loaded[s]);
                 }
             }
         } else if (warp == 13 && lane == 0) {
@@ -195,6 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
             constexpr uint32_t A_LBO = ROWS * Cfg::ROW_BYTES, B_LBO = N * 16, SBO = 128;
             uint64_t* const opbar = HALF ? loaded : ready;      // no converter stage for pre-split operands
             uint32_t it = 0, tcount = 0;
+            if (WST) mbar_wait(wbar, 0);
             for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
                 const uint32_t b = tcount & 1;
                 mbar_wait(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);
@@ -207,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                     tc_fence_after();
                     TC_TRACE(3, it);
                     const uint32_t Aaddr = smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
-                    const uint32_t Baddr = Aaddr + Cfg::A_BYTES;
+                    const uint32_t Baddr = WST ? smem_u32(wres) + (uint32_t)c * Cfg::B_BYTES : Aaddr + Cfg::A_BYTES;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int ky = tap / 3, kx = tap % 3;
@@ -445,23 +463,24 @@ long long* tc_trace_buffer(int Cin, int Cout, cudaStream_t st) {
     return buf;
 }
 
-template <int N, int R, int TERMS, bool HALF, bool SQZ>
+template <int N, int R, int TERMS, bool HALF, bool SQZ, bool WST = false>
 static int launch_tc_cfg2(const ConvArgs& a, cudaStream_t st);
 template <int N, int R, int TERMS, bool HALF = false>
 static int launch_tc_cfg(const ConvArgs& a, cudaStream_t st) {
     return a.epi <= EPI_SUB ? launch_tc_cfg2<N, R, TERMS, HALF, false>(a, st) : launch_tc_cfg2<N, R, TERMS, HALF, true>(a, st);
 }
-template <int N, int R, int TERMS, bool HALF, bool SQZ>
+template <int N, int R, int TERMS, bool HALF, bool SQZ, bool WST>
 static int launch_tc_cfg2(const ConvArgs& a, cudaStream_t st) {
-    using Cfg = TcCfg<N, R, TERMS, HALF>;
+    using Cfg = TcCfg<N, R, TERMS, HALF, WST>;
     static PerDeviceOnce smem_once;
-    auto kern = conv3x3_tc_kernel<N, R, TERMS, HALF, SQZ>;
+    auto kern = conv3x3_tc_kernel<N, R, TERMS, HALF, SQZ, WST>;
     VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     TcTiles tl;
     tl.n_xt = cdiv(a.Wout, 128); tl.n_yt = cdiv(a.Hout, R); tl.n_ct = a.Cout / N;
     tl.n_tiles = tl.n_xt * tl.n_yt * tl.n_ct;
     tl.trace = (a.epi <= EPI_SUB) ? tc_trace_buffer(a.Cin, a.Cout, st) : nullptr;
-    const int grid = std::min(tl.n_tiles, num_sms());
+    int grid = std::min(tl.n_tiles, num_sms());
+    if (WST) grid -= grid % tl.n_ct;             // a CTA's tiles must all have the same cout tile
     char cls[40];
     snprintf(cls, sizeof(cls), HALF ? "conv3x3_tcH%d %d>%d" : "conv3x3_tc%d %d>%d", TERMS, a.Cin, a.Cout);
     const double px = (double)a.Hout * a.Wout;
@@ -540,6 +559,10 @@ int launch_conv3x3_tc_half(const ConvArgs& a, cudaStream_t st) {
     VST_REQUIRE(tc_half_eligible(a.Cin, a.Cout, 1), "conv3x3_tc_half: shape %d>%d not eligible", a.Cin, a.Cout);
     VST_REQUIRE(a.Hin == a.Hout && a.Win == a.Wout && a.Hin >= 2 && a.Win >= 2, "conv3x3_tc_half is stride 1, H,W >= 2");
     const int N = tc_tile_n(a.Cout);
+    static int wst = -1;
+    if (wst < 0) { const char* e = getenv("VST_TC_WST"); wst = e ? atoi(e) : 1; }
+    if (N == 128 && wst && a.Cin == 64 && a.epi <= EPI_SUB && (a.Cout / N) <= num_sms())
+        return launch_tc_cfg2<128, 2, 2, true, false, true>(a, st);      // resident weights (the 64 -> 256 coupling convs)
     if (N == 128) return launch_tc_cfg<128, 2, 2, true>(a, st);
     if (N == 64) return launch_tc_cfg<64, 4, 2, true>(a, st);
     return launch_tc_cfg<16, 4, 2, true>(a, st);
