@@ -329,10 +329,41 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     if (m == 0) BTC_ACC_END(g.trace, g.bar_id, g.rows);
 }
 
+// MODE of a launch (compile time: the hot instantiation keeps its registers):
+//   BTC_PLAIN      out and res are P4 tensors at the block's own resolution
+//   BTC_OUT_SQZ    the block in front of a stride-2 block stores its result SQUEEZED (space-to-depth,
+//                  models/RevResNet.py:34-37: plane (dy*2+dx)*G + g at (y/2, x/2)), with the border the squeezed-input
+//                  form of the stride-2 conv needs (top row / left column replicated, conv_tch.cu; bottom / right
+//                  reflected so that every border value is finite) — the standalone space_to_depth and
+//                  p4_replicate_topleft launches of the transition disappear
+//   BTC_RES_UNSQZ  the block behind a stride-2 block in the INVERSE pass reads its coupling operand through the
+//                  unsqueeze (depth-to-space, :40-43) addressing from the still squeezed tensor — no depth_to_space launch
+constexpr int BTC_PLAIN = 0, BTC_OUT_SQZ = 1, BTC_RES_UNSQZ = 2;
+
+// store pixel (ys, xs) of a squeezed plane [Hs+2][Ws+2] and the border positions that depend on it
+static __device__ __noinline__ void btc_sqz_border(float4* plane, int Hs, int Ws, int ys, int xs, float4 v) {
+    const int Wps = Ws + 2;
+    // padded rows / columns this pixel feeds: itself, the replicated top / left border (from row / column 0), the
+    // reflected bottom / right border (from row Hs-2 / column Ws-2); a 2-pixel map feeds both borders from pixel 0
+    const int rows[3] = {ys + 1, ys == 0 ? 0 : -1, ys == Hs - 2 ? Hs + 1 : -1};
+    const int cols[3] = {xs + 1, xs == 0 ? 0 : -1, xs == Ws - 2 ? Ws + 1 : -1};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if ((i | j) && rows[i] >= 0 && cols[j] >= 0) plane[(size_t)rows[i] * Wps + cols[j]] = v;
+}
+__device__ __forceinline__ void btc_store_sqz(float4* out, int G, int H, int W, int g, int y, int x, float4 v) {
+    const int Hs = H >> 1, Ws = W >> 1, ys = y >> 1, xs = x >> 1, k = ((y & 1) << 1) | (x & 1);
+    float4* plane = out + (size_t)(k * G + g) * ((size_t)(Hs + 2) * (Ws + 2));
+    plane[(size_t)(ys + 1) * (Ws + 2) + xs + 1] = v;
+    if ((ys == 0) | (ys == Hs - 2) | (xs == 0) | (xs == Ws - 2)) btc_sqz_border(plane, Hs, Ws, ys, xs, v);
+}
+
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int C>
+template <int C, int MODE>
 __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(BlockTcArgs a) {
     using Cfg = BtcCfg<C>;
     constexpr int M = Cfg::M, G = Cfg::G, KS = Cfg::KS, N1 = Cfg::N1, N3 = Cfg::N3, TT = Cfg::TT, NX = Cfg::NX, NT = Cfg::NT;
@@ -626,6 +657,20 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         const bool res_ok = min_ok && has_res;
         const float4* resp = reinterpret_cast<const float4*>(a.res) + (size_t)(half * (CPT / 4)) * plane + (xb0 + 1);
         float4* outp = reinterpret_cast<float4*>(a.out) + (size_t)(half * (CPT / 4)) * plane;
+        const int g_first = half * (CPT / 4);                               // first P4 group of this thread's couts
+        // coupling operand of group g_first + j at image pixel (yy, xb0 + dx)
+        auto res_ld = [&](int j, int yy, int dx) -> float4 {
+            if (MODE == BTC_RES_UNSQZ) {
+                const int xx = xb0 + dx, Hs = H >> 1, Ws = W >> 1, k = ((yy & 1) << 1) | (xx & 1);
+                return reinterpret_cast<const float4*>(a.res)[(size_t)(k * G + g_first + j) * ((size_t)(Hs + 2) * (Ws + 2)) +
+                                                              (size_t)((yy >> 1) + 1) * (Ws + 2) + (xx >> 1) + 1];
+            }
+            return resp[(size_t)j * plane + (size_t)(yy + 1) * Wp + dx];
+        };
+        auto out_st = [&](int j, int yy, int xx, float4 o) {
+            if (MODE == BTC_OUT_SQZ) btc_store_sqz(reinterpret_cast<float4*>(a.out), G, H, W, g_first + j, yy, xx, o);
+            else p4_store(outp + (size_t)j * plane, H, W, yy, xx, o);
+        };
         const float sgn = a.sub ? -1.f : 1.f;
         mbar_wait_a(smem_u32(w_bar), 0u);
         // shared-memory objects as 32-bit shared addresses (explicit ld/st.shared: no generic-address path)
@@ -639,13 +684,13 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         float4 rs[CH / 4], rn[CH / 4];                                       // coupling operand: current / next item
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j)
-            rs[j] = (res_ok && xb0 < W) ? resp[(size_t)j * plane + (size_t)(sg.ya + 1) * Wp] : make_float4(0.f, 0.f, 0.f, 0.f);
+            rs[j] = (res_ok && xb0 < W) ? res_ld(j, sg.ya, 0) : make_float4(0.f, 0.f, 0.f, 0.f);
         BTC_ACC_BEGIN();
 #pragma unroll 1
         for (int y = sg.ya; y < sg.yb; ++y) {
             const int ly = y - sg.ya, sa = ly & (NA3 - 1);
             if (tid == 0) BTC_TRACE(4, 4 * ly);
-            if (has_res && tid < G && y + BTC_PREFETCH_ROWS < sg.yb)
+            if (MODE != BTC_RES_UNSQZ && has_res && tid < G && y + BTC_PREFETCH_ROWS < sg.yb)
                 l2_prefetch(reinterpret_cast<const float4*>(a.res) + (size_t)tid * plane + (size_t)(y + 1 + BTC_PREFETCH_ROWS) * Wp + sg.x0 + 1,
                             (uint32_t)(max(min(NB * Cfg::XO, W - sg.x0), 1) * 16));
             const size_t rowoff = (size_t)(y + 1) * Wp;
@@ -665,7 +710,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                         const bool nin = res_ok && (xb0 + nblk * Cfg::XO < W) && (ny < sg.yb);
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j)
-                            rn[j] = nin ? resp[(size_t)j * plane + (size_t)(ny + 1) * Wp + nblk * Cfg::XO] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            rn[j] = nin ? res_ld(j, ny, nblk * Cfg::XO) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     const uint32_t trow = trow0 + blk * Cfg::ACOLS_BLK + sa * N3;
                     const uint32_t ex = ex_base + (uint32_t)(par * (4 * 2 * C * 4));
@@ -716,7 +761,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                             const float4 rr = rs[j];
                             float4 o;
                             o.x = rr.x + v1[4 * j]; o.y = rr.y + v1[4 * j + 1]; o.z = rr.z + v1[4 * j + 2]; o.w = rr.w + v1[4 * j + 3];
-                            p4_store(outp + (size_t)j * plane, H, W, y, x, o);
+                            out_st(j, y, x, o);
                         }
                     }
                     if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 4);
@@ -728,7 +773,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                 const int x = xb0;
                 const bool xin = min_ok && (x < W);
 #pragma unroll
-                for (int j = 0; j < CH / 4; ++j) rs[j] = (xin && has_res) ? resp[(size_t)j * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < CH / 4; ++j) rs[j] = (xin && has_res) ? res_ld(j, y, 0) : make_float4(0.f, 0.f, 0.f, 0.f);
                 BTC_WAIT(b3_full + 8 * sa, (uint32_t)((ly >> (NA3 - 1)) & 1));
                 tc_fence_after();
                 if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
@@ -761,7 +806,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                     if (c0 + CH < CPT) {        // next cout chunk of this row
 #pragma unroll
                         for (int j = 0; j < CH / 4; ++j)
-                            rn[j] = (xin && has_res) ? resp[(size_t)((c0 + CH) / 4 + j) * plane + rowoff] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            rn[j] = (xin && has_res) ? res_ld((c0 + CH) / 4 + j, y, 0) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     float el[CH], er[CH], bb[CH];
 #pragma unroll
@@ -799,7 +844,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                             const float4 rr = rs[j];
                             float4 o;
                             o.x = rr.x + v1[4 * j]; o.y = rr.y + v1[4 * j + 1]; o.z = rr.z + v1[4 * j + 2]; o.w = rr.w + v1[4 * j + 3];
-                            p4_store(outp + (size_t)(c0 / 4 + j) * plane, H, W, y, x, o);
+                            out_st(c0 / 4 + j, y, x, o);
                         }
                     }
                     if (c0 + CH < CPT) {
@@ -821,11 +866,11 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
     }
 }
 
-template <int C>
+template <int C, int MODE>
 static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
     using Cfg = BtcCfg<C>;
     static PerDeviceOnce smem_once;
-    auto kern = rev_block_tc_kernel<C>;
+    auto kern = rev_block_tc_kernel<C, MODE>;
     VST_CUDA_OK(ensure_dyn_smem(smem_once, kern, (int)Cfg::SMEM));
     a.n_strips = cdiv(a.W, Cfg::NB * Cfg::XO);
     int nseg = std::max(1, num_sms() / a.n_strips);
@@ -842,13 +887,17 @@ static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
 }
 
 int launch_rev_block_tc(int C, const float* x, const float* res, float* out, const float* wpack, int H, int W, int sub,
-                        int* status, cudaStream_t st) {
+                        int* status, cudaStream_t st, int mode) {
     VST_REQUIRE(C == 16 || C == 64, "rev_block_tc: C = %d not supported", C);
     VST_REQUIRE(H >= 2 && W >= 4, "rev_block_tc: map %dx%d too small", H, W);
+    VST_REQUIRE(mode == BTC_PLAIN || (H % 2 == 0 && W % 2 == 0 && H >= 4 && W >= 4 && res != nullptr && res != out),
+                "rev_block_tc: squeeze modes need even H, W >= 4 and a coupling operand that does not alias out");
     BlockTcArgs a;
     a.x = x; a.res = res; a.out = out; a.wpack = reinterpret_cast<const uint8_t*>(wpack);
     a.H = H; a.W = W; a.sub = sub; a.status = status; a.n_strips = 0; a.rows_per_seg = 0; a.trace = nullptr; a.trace_cta = 0;
-    return C == 16 ? launch_block_tc_cfg<16>(a, st) : launch_block_tc_cfg<64>(a, st);
+    if (mode == BTC_OUT_SQZ) return C == 16 ? launch_block_tc_cfg<16, BTC_OUT_SQZ>(a, st) : launch_block_tc_cfg<64, BTC_OUT_SQZ>(a, st);
+    if (mode == BTC_RES_UNSQZ) return C == 16 ? launch_block_tc_cfg<16, BTC_RES_UNSQZ>(a, st) : launch_block_tc_cfg<64, BTC_RES_UNSQZ>(a, st);
+    return C == 16 ? launch_block_tc_cfg<16, BTC_PLAIN>(a, st) : launch_block_tc_cfg<64, BTC_PLAIN>(a, st);
 }
 
 }  // namespace vst

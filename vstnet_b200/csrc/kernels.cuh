@@ -150,8 +150,10 @@ bool block_tc_eligible(int C, int mult);
 size_t block_tc_pack_floats(int C);
 int launch_pack_block_tc(int C, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                          const float* b3, float* pk, cudaStream_t st);
+// mode 0: plain; 1: store the result squeezed (the block in front of a stride-2 block, forward); 2: read the coupling
+// operand through the unsqueeze addressing (the block behind a stride-2 block, inverse) — block_tc.cu
 int launch_rev_block_tc(int C, const float* x, const float* res, float* out, const float* wpack, int H, int W, int sub,
-                        int* status, cudaStream_t st);
+                        int* status, cudaStream_t st, int mode = 0);
 
 // tensor-core (tcgen05) path, conv_tc.cu
 bool tc_eligible(int Cin, int Cout, int stride);

@@ -89,6 +89,8 @@ static bool block_fused_tc(const vst_revnet* n, const BlockDesc& b) {
 
 struct Shape { int c, h, w; };
 
+// VST_SQZ_FUSE=0 (developer knob) keeps the standalone space_to_depth / depth_to_space launches of the transitions
+
 // VST_FOLD0=0 (developer knob) keeps the first block as an ordinary launch
 static bool fold_first_block(const vst_revnet* n, int W) {
     static int v = -1;
@@ -215,12 +217,15 @@ static bool block_s2tc(const vst_revnet* n, const BlockDesc& b) {
 }
 
 // x_sq: for stride-2 blocks in f16x2 mode, squeeze(x) with its top/left border replicated (see conv_tch.cu)
+// btc_mode: layout mode of the fused tensor-core block (block_tc.cu): 0 plain, 1 squeezed output, 2 squeezed coupling operand
 static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, const float* x, int Hin, int Win,
                  const Workspace& ws, const float* res, float* out, int epi, cudaStream_t st,
-                 const float* x_sq = nullptr) {
+                 const float* x_sq = nullptr, int btc_mode = 0) {
     const int Ho = Hin / b.stride, Wo = Win / b.stride;
     if (block_fused_tc(n, b) && (epi == EPI_ADD || epi == EPI_SUB) && Win >= 4)
-        return launch_rev_block_tc(b.channel, x, res, out, packed + b.pk_blk, Hin, Win, epi == EPI_SUB ? 1 : 0, ws.status, st);
+        return launch_rev_block_tc(b.channel, x, res, out, packed + b.pk_blk, Hin, Win, epi == EPI_SUB ? 1 : 0, ws.status, st,
+                                   btc_mode);
+    VST_REQUIRE(btc_mode == 0, "internal: squeeze modes need the fused tensor-core block");
     if (b.stride == 1 && b.conv[0].Cin == 16 && b.conv[0].Cout == 4 && b.conv[2].Cout == 16 &&
         (epi == EPI_ADD || epi == EPI_SUB)) {
         // full-resolution stage: the whole block in one fused CUDA-core kernel (block16.cu)
@@ -243,6 +248,18 @@ static int run_F(const vst_revnet* n, const BlockDesc& b, const float* packed, c
     if (run_conv(n, b.conv[1], packed, ws.T1, Ho, Wo, ws.T2, nullptr, EPI_RELU, ws.status, st, split, false)) return 1;
     if (run_conv(n, b.conv[2], packed, ws.T2, Ho, Wo, out, res, epi, ws.status, st, false, split)) return 1;
     return 0;
+}
+
+static bool sqz_fuse_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VST_SQZ_FUSE"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+// the stride-2 block `s2` has a fused tensor-core stride-1 neighbour `nb` working at the un-squeezed resolution h x w:
+// that neighbour can write (forward) / read (inverse) the squeezed layout itself
+static bool sqz_fusable(const vst_revnet* n, const BlockDesc& s2, const BlockDesc& nb, int h, int w) {
+    return sqz_fuse_enabled() && block_s2tc(n, s2) && nb.stride == 1 && block_fused_tc(n, nb) && h % 2 == 0 && w % 2 == 0 &&
+           h >= 4 && w >= 4;
 }
 
 // the two half-states of the network between encode and decode (what channel_reduction's spread loops turn into z)
@@ -288,13 +305,30 @@ static int encode_state(const vst_revnet* n, const float* packed, const FrameIO&
     }
 
     int c = n->c0, h = H, w = W;
+    bool s1_squeezed = false;                       // s1 already holds squeeze(s1) (written so by the previous block)
     for (size_t bi = first_block; bi < n->stack.size(); ++bi) {
         const BlockDesc& b = n->stack[bi];
         if (b.stride == 1) {
+            if (bi + 1 < n->stack.size() && n->stack[bi + 1].stride == 2 && sqz_fusable(n, n->stack[bi + 1], b, h, w) &&
+                bi >= first_block) {
+                // the block in front of a transition stores y = s0 + F(s1) SQUEEZED into the spare buffer (it cannot be in
+                // place: the layouts differ); s0's old buffer becomes the spare one
+                if (run_F(n, b, packed, s1, h, w, ws, s0, spare, EPI_ADD, st, nullptr, 1)) return 1;
+                float* old_s0 = s0;
+                s0 = s1; s1 = spare; spare = old_s0;       // (s0, s1) = (x2, squeeze(y))
+                s1_squeezed = true;
+                continue;
+            }
             if (run_F(n, b, packed, s1, h, w, ws, s0, s0, EPI_ADD, st)) return 1;
             std::swap(s0, s1);
         } else {
-            if (block_s2tc(n, b)) {
+            if (s1_squeezed) {
+                // s1 is already squeeze(x2) with the border the stride-2 conv needs: y1 = F(x2) + squeeze(s0) -> spare
+                if (run_F(n, b, packed, nullptr, h, w, ws, s0, spare, EPI_ADD_SQZ, st, s1)) return 1;
+                float* old_s0 = s0;
+                s0 = s1; s1 = spare; spare = old_s0;       // (s0, s1) = (squeeze(x2), y1)
+                s1_squeezed = false;
+            } else if (block_s2tc(n, b)) {
                 // new x1 = squeeze(s1) -> spare first: the stride-2 conv then runs on it (tensor cores);
                 // y1 = F(s1) + squeeze(s0) -> the now dead s1 buffer
                 if (launch_space_to_depth(s1, spare, c, h, w, st)) return 1;
@@ -344,19 +378,38 @@ static int decode_state(const vst_revnet* n, const float* packed, StatePair sp, 
         std::swap(s0, s1);
     }
     int c = n->c_last;   // channel_reduction's pad channels are dropped by simply ignoring them
+    bool s1_squeezed = false;                // s1 still holds squeeze(x2): the next block reads it through the unsqueeze addressing
     for (int i = (int)n->stack.size() - 1; i >= 0; --i) {
         const BlockDesc& b = n->stack[i];
         if (b.stride == 1) {
+            if (s1_squeezed) {
+                // x1' = unsqueeze(s1) - F(s0) -> spare (not in place: the layouts differ); the squeezed buffer is then free
+                if (run_F(n, b, packed, s0, h, w, ws, s1, spare, EPI_SUB, st, nullptr, 2)) return 1;
+                float* old_s1 = s1;
+                s1 = s0; s0 = spare; spare = old_s1;       // swap included: (s0, s1) = (x1', old s0)
+                s1_squeezed = false;
+                continue;
+            }
             if (run_F(n, b, packed, s0, h, w, ws, s1, s1, EPI_SUB, st)) return 1;
             std::swap(s0, s1);
         } else {
-            // x2 = unsqueeze(s0) -> spare ; x1 = unsqueeze(s1 - F(x2)) -> old s0 buffer
-            if (launch_depth_to_space(s0, spare, c / 4, h, w, st)) return 1;
             const bool sq = block_s2tc(n, b);          // F's stride-2 conv reads the squeezed x2 (= s0) directly
-            if (sq && launch_p4_replicate_topleft(s0, c, h, w, st)) return 1;
-            if (run_F(n, b, packed, spare, 2 * h, 2 * w, ws, s1, s0, EPI_SUB_UNSQZ, st, sq ? s0 : nullptr)) return 1;
-            float* old_s1 = s1;
-            s1 = spare; spare = old_s1;      // (s0, s1) = (x1, x2)
+            if (sq && i > 0 && sqz_fusable(n, b, n->stack[i - 1], 2 * h, 2 * w)) {
+                // x2 stays squeezed in s0's buffer (the next block un-squeezes it on the fly);
+                // x1 = unsqueeze(s1 - F(x2)) -> spare
+                if (launch_p4_replicate_topleft(s0, c, h, w, st)) return 1;
+                if (run_F(n, b, packed, nullptr, 2 * h, 2 * w, ws, s1, spare, EPI_SUB_UNSQZ, st, s0)) return 1;
+                float* old_s1 = s1;
+                s1 = s0; s0 = spare; spare = old_s1;       // (s0, s1) = (x1, squeeze(x2))
+                s1_squeezed = true;
+            } else {
+                // x2 = unsqueeze(s0) -> spare ; x1 = unsqueeze(s1 - F(x2)) -> old s0 buffer
+                if (launch_depth_to_space(s0, spare, c / 4, h, w, st)) return 1;
+                if (sq && launch_p4_replicate_topleft(s0, c, h, w, st)) return 1;
+                if (run_F(n, b, packed, spare, 2 * h, 2 * w, ws, s1, s0, EPI_SUB_UNSQZ, st, sq ? s0 : nullptr)) return 1;
+                float* old_s1 = s1;
+                s1 = spare; spare = old_s1;      // (s0, s1) = (x1, x2)
+            }
             c /= 4; h *= 2; w *= 2;
         }
     }
