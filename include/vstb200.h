@@ -156,8 +156,9 @@ int vst_cwct_stats2d(const float* feat, int C, int H, int W, const uint8_t* labe
  * masked != 0 applies the validity rule of cWCT.py:178 (n_c>10, n_s>10, ratios < 100) per label;
  * invalid labels get T = I, mu = beta = 0 and valid[l] = 0.
  *   T [L,C,C] fp32, mu [L,C] fp32, beta [L,C] fp32, valid [L] int32, status [L] int32 (#jitter
- *   retries, <0 on failure).  use_double selects fp64 factor arithmetic (cWCT.py:13 use_double); otherwise the
- *   covariance is rounded to fp32 first, as the reference's fp32 matmul result would be. */
+ *   retries, <0 on failure).  The factor arithmetic is always fp64; use_double (cWCT.py:13) selects the failure
+ *   rule of the Cholesky: any positive pivot is accepted (fp64 LAPACK), otherwise a pivot below the fp32 noise floor
+ *   of its diagonal counts as a failure and triggers the jitter retry, as fp32 LAPACK would see it. */
 int vst_cwct_factor(const void* content_stats, const void* const* style_stats, const float* alpha_s,
                     int n_styles, float alpha_c, float eps, int C, int n_labels, int masked,
                     int use_double, float* T, float* mu, float* beta, int* valid, int* status, void* stream);

@@ -172,7 +172,13 @@ def test_cwct_rank_deficient_label_uses_jitter(dev):
     out = cw.transfer(zc.to(dev).clone(), zs.to(dev), cm, sm)
     st = cw.last_status.cpu().tolist()
     assert st[0] == 0 and st[1] >= 2, "label 1 should need one jitter retry on each side (got %s)" % st
-    assert maxdiff(out, ref) <= 2e-3
+    # the same transfer evaluated in fp64 with the same jitter count: the reference's fp32 LAPACK result and ours both
+    # sit within 1e-4 of it (fp32 vs fp64 differ by 1.4e-5 on this case)
+    truth = O.cwct_transfer_seg(zc.double(), zs.double(), cm, sm)
+    print("jitter path: retries %s, |cuda - oracle fp32| %.2e, |cuda - fp64| %.2e, |oracle fp32 - fp64| %.2e" % (
+        st, maxdiff(out, ref), maxdiff(out, truth), float((ref.double() - truth).abs().max())))
+    assert maxdiff(out, truth) <= 1e-4
+    assert maxdiff(out, ref) <= 1e-4 + float((ref.double() - truth).abs().max())
 
 
 def test_cwct_c16_generic_channels(dev):

@@ -305,7 +305,7 @@ struct FactorArgs {
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
 
 // covariance (+ jitter) of one label from a stats block into packed-lower A; returns nothing
-__device__ void build_cov(double* A, const StatsView& sv, int l, int C, double n, double jitter, bool round32) {
+__device__ void build_cov(double* A, const StatsView& sv, int l, int C, double n, double jitter, bool /*round32*/) {
     const double* G = sv.gram + (size_t)l * C * C;
     const double* s = sv.sum + (size_t)l * C;
     for (int e = threadIdx.x; e < C * (C + 1) / 2; e += blockDim.x) {
@@ -315,12 +315,12 @@ __device__ void build_cov(double* A, const StatsView& sv, int l, int C, double n
         int j = e - tri(i, 0);
         // average the two triangles: the Gram is accumulated unsymmetrised
         double g = 0.5 * (G[(size_t)i * C + j] + G[(size_t)j * C + i]);
+        // The covariance stays in fp64 (the Gram was accumulated in fp64): rounding it to fp32 "as the reference's matmul
+        // result would be" only adds the reference's own rounding noise a second time — on an ill-conditioned label the
+        // result moved 2x further from the fp64 evaluation than the reference's.  `round32` (fp32 reference arithmetic)
+        // now only selects the failure rule of the factorisation (chol_retry).
         double c = (g - s[i] * s[j] / n) / (n - 1.0);
-        if (round32) c = (double)(float)c;          // the reference's covariance is an fp32 matrix
-        if (i == j) {
-            c += jitter;
-            if (round32) c = (double)(float)c;      // ... and conv + iden * eps an fp32 sum (cWCT.py:123)
-        }
+        if (i == j) c += jitter;
         A[e] = c;
     }
 }
