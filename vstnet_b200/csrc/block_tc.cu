@@ -39,7 +39,7 @@ struct BtcCfg {
     static constexpr int N3 = 3 * C;                     // UMMA N of conv3
     static constexpr int TT = (M == 4) ? 1 : 2;          // operand terms of a t row (M = 4: hi|lo packed into K)
     static constexpr int NB = (C == 16) ? 2 : 1;         // 128-pixel blocks per CTA step (amortises the per-step barrier traffic)
-    static constexpr int PW = 128, XO = 122;
+    static constexpr int PW = 128, XO = 120;               // 4 windows of 30 outputs (btc_win_rows)
     static constexpr int CHUNK = PW * 16;                // one 8-half K chunk of one row: [pixel][16 B]
     static constexpr int XT = (C / 8) * CHUNK;           // one term of an x row: [C/8 chunks][pixel][16 B]
     static constexpr int X_BLK = 2 * XT;
@@ -57,7 +57,7 @@ struct BtcCfg {
     static constexpr int NA1 = 4, NA2 = 2, NA3 = (C == 64) ? 1 : 2;   // powers of two
     static constexpr int A1 = 0, A2 = A1 + NA1 * N1, A3 = A2 + NA2 * N1, ACOLS_BLK = A3 + NA3 * N3, ACOLS = NB * ACOLS_BLK;
     static constexpr int TMEM_COLS = ACOLS <= 128 ? 128 : ACOLS <= 256 ? 256 : 512;
-    static constexpr int EXCH_FLOATS = 2 * 2 * (4 * 2 * M) + 2 * (4 * 2 * C);   // E1, E2 (double-buffered) + E3
+    static constexpr int EXCH_FLOATS = 2 * 2 * (4 * 2 * M);                     // E1, E2 (double-buffered)
     static constexpr int AUX_BYTES = 512 + EXCH_FLOATS * 4;
     static constexpr size_t SMEM = (size_t)NX * X_SLOT + 2 * (size_t)NT * T_SLOT + WPACK_BYTES + AUX_BYTES + 1024;
     static constexpr int E3W = 16;                           // E3 warps: 4 lane quarters x NPART cout parts (more parallel roles beat
@@ -229,9 +229,22 @@ struct BtcMidArgs {
     uint32_t tring, t_full, t_empty;
     uint32_t bias, exch;
     int nacc, nacc_log2, rows, bar_id, x0, W;
+    int windowed;                  // store the t row in window form (btc_win_rows): E2
     int* status;
     long long* trace;              // tracing builds: wait accounting of this role (nullptr otherwise)
 };
+// Window form of a t2 row (conv3's A operand): operand row 32q + l holds t2 pixel 2 + 30q + l, i.e. every warp of E3
+// (TMEM lanes 32q .. 32q+31) sees a self-contained 32-pixel window whose 30 interior lanes fold kx with shuffles
+// alone — no exchange through shared memory, no barrier.  Pixels on a window seam live in two rows.
+__device__ __forceinline__ void btc_win_rows(int p, int& r0, int& r1) {
+    r0 = r1 = -1;
+    const int w = p - 2;
+    if (w < 0 || w >= 122) return;
+    const int q = min(w / 30, 3), l = w - 30 * q;
+    r0 = 32 * q + l;
+    if (q > 0 && l < 2) r1 = 32 * (q - 1) + 30 + l;
+}
+
 template <int C>
 static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     using Cfg = BtcCfg<C>;
@@ -245,6 +258,13 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
     const uint32_t trow = g.tacc + ((uint32_t)(q * 32) << 16);
     uint32_t par = 0;
     uint32_t hmax = 0u;                         // fp16 range guard (tc_ptx.cuh)
+    int o0 = m, o1 = -1;                        // operand rows of this thread's own pixel
+    if (g.windowed) btc_win_rows(m, o0, o1);
+    // store one pixel's 16-byte operand chunk at operand rows r0 / r1 (negative: none)
+    auto put = [](uint32_t base, int r0, int r1, uint4 v) {
+        if (r0 >= 0) btc_sts128(base + 16 * r0, v);
+        if (r1 >= 0) btc_sts128(base + 16 * r1, v);
+    };
     BTC_ACC_BEGIN();
 #pragma unroll 1
     for (int l = 0; l < g.rows; ++l) {
@@ -256,7 +276,9 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
             const int x = g.x0 + blk * Cfg::XO - 3 + m;
             const bool own = (x >= 0) && (x < g.W);
             const bool mir_l = (x == 1) && (m >= 2), mir_r = (x == g.W - 2) && (m + 2 < Cfg::PW);
-            const uint32_t slot = g.tring + (uint32_t)(st * Cfg::T_SLOT + blk * Cfg::T_BLK + m * 16);
+            const uint32_t slot = g.tring + (uint32_t)(st * Cfg::T_SLOT + blk * Cfg::T_BLK);
+            int ml0 = m - 2, ml1 = -1, mr0 = m + 2, mr1 = -1;            // operand rows of the reflected copies (image edge)
+            if (g.windowed && (mir_l || mir_r)) { btc_win_rows(m - 2, ml0, ml1); btc_win_rows(m + 2, mr0, mr1); }
 #pragma unroll 1
             for (int ps = 0; ps < NPASS; ++ps) {
                 // D columns of this pass: [kx][MP channels]
@@ -308,16 +330,16 @@ static __device__ __noinline__ void btc_mid_epilogue(const BtcMidArgs g) {
                     hmax = range_fold(range_fold(hmax, *reinterpret_cast<const uint32_t*>(&h01)), *reinterpret_cast<const uint32_t*>(&h23));
                     const uint4 v = make_uint4(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23),
                                                btc_pack_half2(o[0] - f01.x, o[1] - f01.y), btc_pack_half2(o[2] - f23.x, o[3] - f23.y));
-                    if (own) btc_sts128(slot, v);
-                    if (mir_l) btc_sts128(slot - 32, v);
-                    if (mir_r) btc_sts128(slot + 32, v);
+                    if (own) put(slot, o0, o1, v);
+                    if (mir_l) put(slot, ml0, ml1, v);
+                    if (mir_r) put(slot, mr0, mr1, v);
                 } else {
                     uint4 hv, lv;
                     btc_split8(o, hv, lv, hmax);
                     const uint32_t ph = slot + ps * Cfg::CHUNK, pl = ph + Cfg::T_TERM;     // term 0 (hi) / term 1 (lo), K chunk ps
-                    if (own) { btc_sts128(ph, hv); btc_sts128(pl, lv); }
-                    if (mir_l) { btc_sts128(ph - 32, hv); btc_sts128(pl - 32, lv); }
-                    if (mir_r) { btc_sts128(ph + 32, hv); btc_sts128(pl + 32, lv); }
+                    if (own) { put(ph, o0, o1, hv); put(pl, o0, o1, lv); }
+                    if (mir_l) { put(ph, ml0, ml1, hv); put(pl, ml0, ml1, lv); }
+                    if (mir_r) { put(ph, mr0, mr1, hv); put(pl, mr0, mr1, lv); }
                 }
             }
         }
@@ -403,7 +425,6 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
     float* exch1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
     float* exch2 = exch1 + 2 * (4 * 2 * M);
-    float* exch3 = exch2 + 2 * (4 * 2 * M);
     const float* bias_s = reinterpret_cast<const float*>(wsm + Cfg::W1_BYTES + Cfg::W2_BYTES + Cfg::W3_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -642,6 +663,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         g.nacc_log2 = second ? 1 : 2;
         g.rows = second ? sg.t2b - sg.t2a + 1 : sg.t1b - sg.t1a + 1;
         g.bar_id = second ? 2 : 1;
+        g.windowed = second ? 1 : 0;
         g.x0 = sg.x0; g.W = W;
         g.status = a.status;
         g.trace = (a.trace && (int)blockIdx.x == a.trace_cta) ? a.trace : nullptr;
@@ -649,9 +671,11 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
     } else {
         // ================= E3: acc3 -> kx fold, bias, coupling with res -> global P4 (+ reflection border) =================
         constexpr int CPT = Cfg::CPT, CH = Cfg::CH, NB = Cfg::NB;
-        const int q = warp & 3, half = warp >> 2, m = q * 32 + lane;       // half = cout part of this warp (0 .. NPART-1)
-        const int xb0 = sg.x0 - 3 + m;                                       // image column of this thread in block 0
-        const bool min_ok = (m >= 3) && (m < 3 + Cfg::XO);
+        // conv3's operand rows are in window form (btc_win_rows): lane l of lane quarter q holds t2 pixel 2 + 30q + l, and
+        // lanes 1 .. 30 produce output pixel 30q + l - 1 of the block from their own and their neighbours' partial sums
+        const int q = warp & 3, half = warp >> 2;                            // half = cout part of this warp (0 .. NPART-1)
+        const int xb0 = sg.x0 + 30 * q + lane - 1;                           // image column of this thread in block 0
+        const bool min_ok = (lane >= 1) && (lane <= 30);
         const size_t plane = (size_t)Hp * Wp;
         const bool has_res = a.res != nullptr;                             // null: the coupling operand is zero (out = +/- F(x))
         const bool res_ok = min_ok && has_res;
@@ -675,12 +699,8 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         mbar_wait_a(smem_u32(w_bar), 0u);
         // shared-memory objects as 32-bit shared addresses (explicit ld/st.shared: no generic-address path)
         const uint32_t b3p = smem_u32(bias_s + 2 * M + half * CPT);          // this thread's couts
-        const uint32_t ex_base = smem_u32(exch3 + half * CPT);
-        const uint32_t pub_off = (uint32_t)((q * 2 + (lane == 0 ? 1 : 0)) * C * 4);   // where lane 31 / lane 0 publish
-        const uint32_t l_off = (uint32_t)(((q > 0 ? q - 1 : 0) * 2 + 0) * C * 4), r_off = (uint32_t)(((q < 3 ? q + 1 : 3) * 2 + 1) * C * 4);
         const uint32_t b3_full = smem_u32(a3_full), b3_empty = smem_u32(a3_empty);
         const uint32_t trow0 = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::A3 + half * CPT;
-        int par = 0;                                                         // exchange buffer parity, toggles per (row, block)
         float4 rs[CH / 4], rn[CH / 4];                                       // coupling operand: current / next item
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j)
@@ -693,7 +713,6 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
             if (MODE != BTC_RES_UNSQZ && has_res && tid < G && y + BTC_PREFETCH_ROWS < sg.yb)
                 l2_prefetch(reinterpret_cast<const float4*>(a.res) + (size_t)tid * plane + (size_t)(y + 1 + BTC_PREFETCH_ROWS) * Wp + sg.x0 + 1,
                             (uint32_t)(max(min(NB * Cfg::XO, W - sg.x0), 1) * 16));
-            const size_t rowoff = (size_t)(y + 1) * Wp;
             if (CPT == CH) {
                 // ---- all of this thread's couts fit in registers: one pass per block.  The coupling operand of the
                 //      NEXT (row, block) item is requested before the current one is processed (rs/rn live across rows)
@@ -701,7 +720,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                 tc_fence_after();
                 if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
 #pragma unroll
-                for (int blk = 0; blk < NB; ++blk, par ^= 1) {
+                for (int blk = 0; blk < NB; ++blk) {
                     const int x = xb0 + blk * Cfg::XO;
                     const bool xin = min_ok && (x < W);
                     {   // next item: block blk+1 of this row, or block 0 of the next row
@@ -713,7 +732,6 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                             rn[j] = nin ? res_ld(j, ny, nblk * Cfg::XO) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     const uint32_t trow = trow0 + blk * Cfg::ACOLS_BLK + sa * N3;
-                    const uint32_t ex = ex_base + (uint32_t)(par * (4 * 2 * C * 4));
                     uint32_t u0[CH], u1[CH], u2[CH];
                     tmem_ld_nowait<CH>(trow + 0 * C, u0);
                     tmem_ld_nowait<CH>(trow + 1 * C, u1);
@@ -728,30 +746,17 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                         tc_fence_before();
                         mbar_arrive_a(b3_empty + 8 * sa);
                     }
-                    if (lane == 31 || lane == 0) {
-#pragma unroll
-                        for (int i = 0; i < CH; i += 4)
-                            btc_sts128(ex + pub_off + 4 * i, lane == 0 ? make_uint4(u2[i], u2[i + 1], u2[i + 2], u2[i + 3])
-                                                                       : make_uint4(u0[i], u0[i + 1], u0[i + 2], u0[i + 3]));
-                    }
-                    if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 1);
-                    named_barrier(3 + half, 128);
                     if (tid == 0) BTC_TRACE(4, 4 * ly + 2);
-                    if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 2);
-                    float el[CH], er[CH], bb[CH];
+                    float bb[CH];
 #pragma unroll
-                    for (int i = 0; i < CH; i += 4) {       // warp-uniform addresses (broadcast), all issued before any use
-                        const float4 a4 = btc_lds128(ex + l_off + 4 * i), c4 = btc_lds128(ex + r_off + 4 * i), d4 = btc_lds128(b3p + 4 * i);
-                        el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
-                        er[i] = c4.x; er[i + 1] = c4.y; er[i + 2] = c4.z; er[i + 3] = c4.w;
+                    for (int i = 0; i < CH; i += 4) {       // warp-uniform addresses (broadcast)
+                        const float4 d4 = btc_lds128(b3p + 4 * i);
                         bb[i] = d4.x; bb[i + 1] = d4.y; bb[i + 2] = d4.z; bb[i + 3] = d4.w;
                     }
 #pragma unroll
-                    for (int i = 0; i < CH; ++i) {
-                        const float ls = __shfl_up_sync(0xffffffffu, v0[i], 1);
-                        const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
-                        const float lv = (lane == 0) ? el[i] : ls;
-                        const float rv = (lane == 31) ? er[i] : rs;
+                    for (int i = 0; i < CH; ++i) {          // lanes 0 / 31 (window halo) compute values nobody stores
+                        const float lv = __shfl_up_sync(0xffffffffu, v0[i], 1);
+                        const float rv = __shfl_down_sync(0xffffffffu, v2[i], 1);
                         v1[i] = sgn * (((lv + v1[i]) + rv) * (1.0f / VST_HALF_SCALE) + bb[i]);
                     }
                     if (tid == 0 && blk == 0) BTC_TRACE(5, 8 * ly + 3);
@@ -778,29 +783,7 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                 tc_fence_after();
                 if (tid == 0) BTC_TRACE(4, 4 * ly + 1);
                 const uint32_t trow = trow0 + sa * N3;
-                const uint32_t ex = ex_base + (uint32_t)(par * (4 * 2 * C * 4));
-                par ^= 1;
-                // ---- phase 1: publish the partial sums the neighbouring warp needs (lane 31's kx=0, lane 0's kx=2)
-#pragma unroll
-                for (int c0 = 0; c0 < CPT; c0 += CH) {
-                    uint32_t u0[CH], u2[CH];
-                    tmem_ld8_nowait(trow + (uint32_t)(0 * C + c0), u0);
-                    tmem_ld8_nowait(trow + (uint32_t)(2 * C + c0), u2);
-                    tmem_ld_wait();
-                    tmem_ld_fence_regs<CH>(u0); tmem_ld_fence_regs<CH>(u2);
-                    float v0[CH], v2[CH];
-#pragma unroll
-                    for (int i = 0; i < CH; ++i) { v0[i] = __uint_as_float(u0[i]); v2[i] = __uint_as_float(u2[i]); }
-                    if (lane == 31 || lane == 0) {
-#pragma unroll
-                        for (int i = 0; i < CH; i += 4)
-                            btc_sts128(ex + pub_off + 4 * (c0 + i), lane == 0 ? make_uint4(u2[i], u2[i + 1], u2[i + 2], u2[i + 3])
-                                                                              : make_uint4(u0[i], u0[i + 1], u0[i + 2], u0[i + 3]));
-                    }
-                }
-                named_barrier(3 + half, 128);
                 if (tid == 0) BTC_TRACE(4, 4 * ly + 2);
-                // ---- phase 2
 #pragma unroll
                 for (int c0 = 0; c0 < CPT; c0 += CH) {
                     if (c0 + CH < CPT) {        // next cout chunk of this row
@@ -808,13 +791,10 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                         for (int j = 0; j < CH / 4; ++j)
                             rn[j] = (xin && has_res) ? res_ld((c0 + CH) / 4 + j, y, 0) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    float el[CH], er[CH], bb[CH];
+                    float bb[CH];
 #pragma unroll
                     for (int i = 0; i < CH; i += 4) {
-                        const float4 a4 = btc_lds128(ex + l_off + 4 * (c0 + i)), c4 = btc_lds128(ex + r_off + 4 * (c0 + i)),
-                                     d4 = btc_lds128(b3p + 4 * (c0 + i));
-                        el[i] = a4.x; el[i + 1] = a4.y; el[i + 2] = a4.z; el[i + 3] = a4.w;
-                        er[i] = c4.x; er[i + 1] = c4.y; er[i + 2] = c4.z; er[i + 3] = c4.w;
+                        const float4 d4 = btc_lds128(b3p + 4 * (c0 + i));
                         bb[i] = d4.x; bb[i + 1] = d4.y; bb[i + 2] = d4.z; bb[i + 3] = d4.w;
                     }
                     uint32_t u0[CH], u1[CH], u2[CH];
@@ -832,10 +812,8 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                     }
 #pragma unroll
                     for (int i = 0; i < CH; ++i) {
-                        const float ls = __shfl_up_sync(0xffffffffu, v0[i], 1);
-                        const float rs = __shfl_down_sync(0xffffffffu, v2[i], 1);
-                        const float lv = (lane == 0) ? el[i] : ls;
-                        const float rv = (lane == 31) ? er[i] : rs;
+                        const float lv = __shfl_up_sync(0xffffffffu, v0[i], 1);
+                        const float rv = __shfl_down_sync(0xffffffffu, v2[i], 1);
                         v1[i] = sgn * (((lv + v1[i]) + rv) * (1.0f / VST_HALF_SCALE) + bb[i]);
                     }
                     if (xin) {
