@@ -74,6 +74,7 @@ struct BtcCfg {
 constexpr int BTC_PREFETCH_ROWS = 3;     // L2 prefetch distance of the x / res row streams (A/B: 3 and 1 equal, -4 % vs 6 or none; 12 is worse)
 
 struct BlockTcArgs {
+    int ko;                    // developer builds (-DBTC_KNOCKOUT): bit 0 no x loads, bit 1 no res loads, bit 2 no stores
     const float* x;        // P4 [C/4][H+2][W+2][4]  half-state F is evaluated on
     const float* res;      // P4, coupling operand (may alias out)
     float* out;            // P4
@@ -603,6 +604,9 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
 #pragma unroll
             for (int g = 0; g < GB; ++g) v[g] = __ldg(src + (size_t)g * plane);
         }
+#ifdef BTC_KNOCKOUT
+        const bool ko_x = a.ko & 1;
+#endif
         BTC_ACC_BEGIN();
 #pragma unroll 1
         for (int rx = sg.xa; rx <= sg.xb; ++rx) {
@@ -628,6 +632,9 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
                     const int nit = (it + 1 == ITEMS) ? 0 : it + 1;
                     const int nrow = min((it + 1 == ITEMS) ? rx + 1 : rx, sg.xb);
                     const float4* src = in4 + (size_t)((nit % NBATCH) * GB) * plane + (size_t)(nrow + 1) * Wp + pcb[nit / NBATCH];
+#ifdef BTC_KNOCKOUT
+                    if (!ko_x)
+#endif
 #pragma unroll
                     for (int g = 0; g < GB; ++g) v[g] = __ldg(src + (size_t)g * plane);
                 }
@@ -677,7 +684,12 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
         const int xb0 = sg.x0 + 30 * q + lane - 1;                           // image column of this thread in block 0
         const bool min_ok = (lane >= 1) && (lane <= 30);
         const size_t plane = (size_t)Hp * Wp;
+#ifdef BTC_KNOCKOUT
+        const bool has_res = a.res != nullptr && !(a.ko & 2);
+        const bool ko_st = a.ko & 4;
+#else
         const bool has_res = a.res != nullptr;                             // null: the coupling operand is zero (out = +/- F(x))
+#endif
         const bool res_ok = min_ok && has_res;
         const float4* resp = reinterpret_cast<const float4*>(a.res) + (size_t)(half * (CPT / 4)) * plane + (xb0 + 1);
         float4* outp = reinterpret_cast<float4*>(a.out) + (size_t)(half * (CPT / 4)) * plane;
@@ -692,6 +704,9 @@ __global__ void __launch_bounds__(BtcCfg<C>::THREADS, 1) rev_block_tc_kernel(Blo
             return resp[(size_t)j * plane + (size_t)(yy + 1) * Wp + dx];
         };
         auto out_st = [&](int j, int yy, int xx, float4 o) {
+#ifdef BTC_KNOCKOUT
+            if (ko_st && o.x != 12345.678f) return;
+#endif
             if (MODE == BTC_OUT_SQZ) btc_store_sqz(reinterpret_cast<float4*>(a.out), G, H, W, g_first + j, yy, xx, o);
             else p4_store(outp + (size_t)j * plane, H, W, yy, xx, o);
         };
@@ -856,6 +871,9 @@ static int launch_block_tc_cfg(BlockTcArgs a, cudaStream_t st) {
     if (a.rows_per_seg < 8) a.rows_per_seg = std::min(8, a.H);
     nseg = cdiv(a.H, a.rows_per_seg);
     a.trace = tc_trace_buffer(1000 + C, 0, st);
+#ifdef BTC_KNOCKOUT
+    { const char* e = getenv("VST_BTC_KO"); a.ko = e ? atoi(e) : 0; }
+#endif
     a.trace_cta = std::min(a.n_strips * nseg - 1, a.n_strips * (nseg / 2) + a.n_strips / 2);
     const double px = (double)a.H * a.W;
     ProfScope prof(st, C == 16 ? "rev_block_tc 16>4>4>16" : "rev_block_tc 64>16>16>64",
@@ -872,7 +890,7 @@ int launch_rev_block_tc(int C, const float* x, const float* res, float* out, con
                 "rev_block_tc: squeeze modes need even H, W >= 4 and a coupling operand that does not alias out");
     BlockTcArgs a;
     a.x = x; a.res = res; a.out = out; a.wpack = reinterpret_cast<const uint8_t*>(wpack);
-    a.H = H; a.W = W; a.sub = sub; a.status = status; a.n_strips = 0; a.rows_per_seg = 0; a.trace = nullptr; a.trace_cta = 0;
+    a.ko = 0; a.H = H; a.W = W; a.sub = sub; a.status = status; a.n_strips = 0; a.rows_per_seg = 0; a.trace = nullptr; a.trace_cta = 0;
     if (mode == BTC_OUT_SQZ) return C == 16 ? launch_block_tc_cfg<16, BTC_OUT_SQZ>(a, st) : launch_block_tc_cfg<64, BTC_OUT_SQZ>(a, st);
     if (mode == BTC_RES_UNSQZ) return C == 16 ? launch_block_tc_cfg<16, BTC_RES_UNSQZ>(a, st) : launch_block_tc_cfg<64, BTC_RES_UNSQZ>(a, st);
     return C == 16 ? launch_block_tc_cfg<16, BTC_PLAIN>(a, st) : launch_block_tc_cfg<64, BTC_PLAIN>(a, st);
