@@ -53,7 +53,12 @@ struct TcCfg {
     static constexpr int B_BYTES = TW * B_TERM_BYTES;
     static constexpr int WST_CHUNKS = 4;            // resident weight chunks (Cin = 64)
     static constexpr int W_RES_BYTES = WST ? WST_CHUNKS * B_BYTES : 0;
-    static constexpr int STAGE_BYTES = WST ? A_BYTES : A_BYTES + B_BYTES;
+    // TSPLIT (WST with two activation terms): a pipeline stage carries ONE term (hi or lo) of a chunk, i.e. the 66 KB
+    // that remain beside the resident weights form 4 stages of 16.6 KB instead of 2 of 33 KB.  A stage's TMA fill takes
+    // ~3.4 k cycles against ~2.2 k cycles of UMMAs per chunk (role trace), so two stages cannot hide it; four do.
+    static constexpr bool TSPLIT = WST && TA == 2;
+    static constexpr int NSUB = TSPLIT ? 2 : 1;     // pipeline stages per chunk
+    static constexpr int STAGE_BYTES = TSPLIT ? A_TERM_BYTES : WST ? A_BYTES : A_BYTES + B_BYTES;
     static constexpr int AUX_BYTES = 2048;          // barriers (1 KB) + bias (<= 256 floats)
     static constexpr int NS_FIT = (226 * 1024 - AUX_BYTES - W_RES_BYTES) / STAGE_BYTES;
     static constexpr int NS = NS_FIT > 4 ? 4 : NS_FIT;
@@ -121,6 +126,12 @@ __device__ __forceinline__ void umma_f16_tc(uint32_t d_tmem, uint64_t a_desc, ui
         : "memory");
 }
 
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // HALF = true: the input is an H8 split-half tensor (kernels.cuh): hi and lo rows arrive by TMA already in
 // the K-major fp16 operand layout, there is no converter stage, and the UMMAs are kind::f16 with K = 16.
 template <int N, int R, int TERMS, bool HALF, bool SQZ, bool WST = false>
@@ -182,15 +193,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                 const int ct = t % tl.n_ct, rest = t / tl.n_ct;
                 const int x0 = (rest % tl.n_xt) * 128, y0 = (rest / tl.n_xt) * R;
                 const float* wsrc = a.w + (size_t)ct * n_chunks * (Cfg::B_BYTES / 4);
-                for (int c = 0; c < n_chunks; ++c, ++it) {
+                for (int c = 0; c < n_chunks; ++c)
+#pragma unroll
+                for (int sub = 0; sub < Cfg::NSUB; ++sub, ++it) {
                     const int s = it % NS;
                     mbar_wait(&empty[s], ((it / NS) & 1) ^ 1);
                     TC_TRACE(0, it);
                     uint8_t* A = stage_base + (size_t)s * Cfg::STAGE_BYTES;
-                    constexpr int NT = HALF ? Cfg::TA : 1;            // tensors to fetch: raw fp32 | hi, lo
+                    constexpr int NT = Cfg::TSPLIT ? 1 : HALF ? Cfg::TA : 1;   // tensors per stage: one term | raw fp32 | hi, lo
                     mbar_arrive_expect_tx(&loaded[s], NT * Cfg::A_TERM_BYTES + (WST ? 0 : Cfg::B_BYTES));
 #pragma unroll
-                    for (int term = 0; term < NT; ++term) {
+                    for (int tt = 0; tt < NT; ++tt) {
+                        const int term = Cfg::TSPLIT ? sub : tt;
                         // H8: the lo planes follow the Cin/8 hi planes; both are addressed like P4 groups
                         const float4* src = in4 + (size_t)term * (a.Cin / 8) * Hp * Wp;
 #pragma unroll
@@ -198,61 +212,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
 #pragma unroll
                             for (int row = 0; row < ROWS; ++row) {
                                 const int py = min(y0 + row, Hp - 1);     // padded row of image row y0-1+row
-                                bulk_g2s(A + term * Cfg::A_TERM_BYTES + (g * ROWS + row) * Cfg::ROW_BYTES,
+                                bulk_g2s(A + tt * Cfg::A_TERM_BYTES + (g * ROWS + row) * Cfg::ROW_BYTES,
                                          src + ((size_t)(2 * c + g) * Hp + py) * Wp + x0, Cfg::ROW_BYTES, &loaded[s]);
                             }
                     }
                     if (!WST) bulk_g2s(A + Cfg::A_BYTES, wsrc + (size_t)c * (Cfg::B_BYTES / 4), Cfg::B_BYTES, &loaded[s]);
                 }
             }
-        } else if (warp == 13 && lane == 0) {
+        } else if (warp == 13) {
             // ================= UMMA issuer =================
+            // The whole warp walks the (warp-uniform) schedule and one elected lane issues the tcgen05 instructions:
+            // issued from a divergent single-lane branch, every UTCHMMA is wrapped in an election loop and its
+            // descriptors are rebuilt through the vector registers — ~12 instructions per UMMA, which paced this role at
+            // 70-95 cycles per UMMA against the tensor pipe's 64 (role trace).  Descriptors are constant high bits +
+            // (shared address >> 4): one 64-bit add per operand.
             // instruction descriptor: D = F32 (bit 4); A, B = TF32 (format 2) | F16 (format 0); N at bit 17, M at bit 24
             constexpr uint32_t IDESC = (1u << 4) | (HALF ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t A_LBO = ROWS * Cfg::ROW_BYTES, B_LBO = N * 16, SBO = 128;
             uint64_t* const opbar = HALF ? loaded : ready;      // no converter stage for pre-split operands
+            const bool el = tc_elect_one();
+            const uint64_t dA0 = make_desc(smem_u32(stage_base), A_LBO, SBO);
+            const uint64_t dB0 = make_desc(WST ? smem_u32(wres) : smem_u32(stage_base) + Cfg::A_BYTES, B_LBO, SBO);
             uint32_t it = 0, tcount = 0;
             if (WST) mbar_wait(wbar, 0);
             for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
                 const uint32_t b = tcount & 1;
                 mbar_wait(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
-                TC_TRACE(5, tcount);
+                if (lane == 0) TC_TRACE(5, tcount);
                 const uint32_t acc = tmem_base + b * Cfg::ACC_COLS;
-                for (int c = 0; c < n_chunks; ++c, ++it) {
+                for (int c = 0; c < n_chunks; ++c)
+#pragma unroll
+                for (int sub = 0; sub < Cfg::NSUB; ++sub, ++it) {
                     const int s = it % NS;
                     mbar_wait(&opbar[s], (it / NS) & 1);
                     tc_fence_after();
-                    TC_TRACE(3, it);
-                    const uint32_t Aaddr = smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
-                    const uint32_t Baddr = WST ? smem_u32(wres) + (uint32_t)c * Cfg::B_BYTES : Aaddr + Cfg::A_BYTES;
+                    if (lane == 0) TC_TRACE(3, it);
+                    const uint64_t dA = dA0 + (uint64_t)((uint32_t)s * (Cfg::STAGE_BYTES >> 4));
+                    const uint64_t dB = WST ? dB0 + (uint64_t)((uint32_t)c * (Cfg::B_BYTES >> 4)) : dB0 + (uint64_t)((uint32_t)s * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int ky = tap / 3, kx = tap % 3;
-                        const uint64_t bh = make_desc(Baddr + tap * 2 * N * 16, B_LBO, SBO);
+                        const uint64_t bh = dB + (uint64_t)((tap * 2 * N * 16) >> 4);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const uint32_t aoff = ((r + ky) * PW + kx) * 16;
+                            const uint64_t ah = dA + (uint64_t)((((r + ky) * PW + kx) * 16) >> 4);
                             const uint32_t d = acc + r * N;
-                            const uint32_t first = (c > 0 || tap > 0) ? 1u : 0u;
-                            if (HALF) {
-                                umma_f16_tc(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
-                                if (TERMS >= 2)
-                                    umma_f16_tc(d, make_desc(Aaddr + Cfg::A_TERM_BYTES + aoff, A_LBO, SBO), bh, IDESC, 1u);
-                            } else {
-                                umma_tf32(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
-                                if (TERMS >= 2)
-                                    umma_tf32(d, make_desc(Aaddr + Cfg::A_TERM_BYTES + aoff, A_LBO, SBO), bh, IDESC, 1u);
-                                if (TERMS >= 3)
-                                    umma_tf32(d, make_desc(Aaddr + aoff, A_LBO, SBO),
-                                              make_desc(Baddr + Cfg::B_TERM_BYTES + tap * 2 * N * 16, B_LBO, SBO), IDESC, 1u);
+                            const uint32_t first = (c > 0 || sub > 0 || tap > 0) ? 1u : 0u;
+                            if (el) {
+                                if (Cfg::TSPLIT) {
+                                    umma_f16_tc(d, ah, bh, IDESC, first);     // this stage's term
+                                } else if (HALF) {
+                                    umma_f16_tc(d, ah, bh, IDESC, first);
+                                    if (TERMS >= 2) umma_f16_tc(d, ah + (uint64_t)(Cfg::A_TERM_BYTES >> 4), bh, IDESC, 1u);
+                                } else {
+                                    umma_tf32(d, ah, bh, IDESC, first);
+                                    if (TERMS >= 2) umma_tf32(d, ah + (uint64_t)(Cfg::A_TERM_BYTES >> 4), bh, IDESC, 1u);
+                                    if (TERMS >= 3) umma_tf32(d, ah, bh + (uint64_t)(Cfg::B_TERM_BYTES >> 4), IDESC, 1u);
+                                }
                             }
                         }
                     }
-                    umma_commit(&empty[s]);      // smem stage reusable once these UMMAs have read it
-                    TC_TRACE(4, it);
+                    if (el) umma_commit(&empty[s]);      // smem stage reusable once these UMMAs have read it
+                    if (lane == 0) TC_TRACE(4, it);
                 }
-                umma_commit(&acc_full[b]);       // this tile's accumulators are complete
+                if (el) umma_commit(&acc_full[b]);       // this tile's accumulators are complete
             }
         }
         __syncwarp();

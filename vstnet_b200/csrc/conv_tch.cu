@@ -225,44 +225,50 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
         }
     } else if (warp == W_MMA) {
         // ================= UMMA issuer =================
-        if (lane == 0) {
+        // the whole warp walks the warp-uniform schedule, one elected lane issues (see conv_tc.cu); descriptors are
+        // constant high bits + (shared address >> 4)
+        {
             // kind::f16: D = F32 (bit 4), A = B = F16 (format 0), N at bit 17, M at bit 24
             constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((128u >> 4) << 24);
             constexpr uint32_t A_LBO = ROWS * Cfg::ROW_BYTES, B_LBO = NP * 16, SBO = 128;     // A: 4 image rows = 128 contiguous operand rows
+            uint32_t elp;
+            asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(elp));
+            const bool el = elp != 0;
+            const uint64_t dA0 = make_desc(smem_u32(op_base), A_LBO, SBO);
+            const uint64_t dB0 = make_desc(smem_u32(op_base) + Cfg::A_BYTES, B_LBO, SBO);
             uint32_t it = 0, tcount = 0;
             for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
                 const uint32_t b = tcount % NACC;
                 mbar_wait(&acc_empty[b], ((tcount / NACC) & 1) ^ 1);
                 tc_fence_after();
-                TCH_TRACE(5, tcount);
+                if (lane == 0) TCH_TRACE(5, tcount);
                 const uint32_t acc = tmem_base + b * Cfg::ACC_COLS;
                 for (int c = 0; c < n_chunks; ++c, ++it) {
                     const int o = it % NO;
                     mbar_wait(&op_ready[o], (it / NO) & 1);
                     tc_fence_after();
-                    TCH_TRACE(3, it);
-                    const uint32_t Aaddr = smem_u32(op_base + (size_t)o * Cfg::OP_BYTES);
-                    const uint32_t Baddr = Aaddr + Cfg::A_BYTES;
+                    if (lane == 0) TCH_TRACE(3, it);
+                    const uint64_t so = (uint64_t)((uint32_t)o * (Cfg::OP_BYTES >> 4));
+                    const uint64_t dA = dA0 + so, dB = dB0 + so;
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
-                        const uint64_t bh = make_desc(Baddr + ky * 2 * NP * 16, B_LBO, SBO);
+                        const uint64_t bh = dB + (uint64_t)((ky * 2 * NP * 16) >> 4);
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            const uint32_t aoff = (4 * r + ky) * Cfg::ROW_BYTES;
+                            const uint64_t ah = dA + (uint64_t)(((4 * r + ky) * Cfg::ROW_BYTES) >> 4);
                             const uint32_t d = acc + r * NP;
                             const uint32_t first = (c > 0 || ky > 0) ? 1u : 0u;
-                            umma_f16(d, make_desc(Aaddr + aoff, A_LBO, SBO), bh, IDESC, first);
-                            if (TERMS >= 2)
-                                umma_f16(d, make_desc(Aaddr + Cfg::A_TERM_BYTES + aoff, A_LBO, SBO), bh, IDESC, 1u);
-                            if (TERMS >= 3)
-                                umma_f16(d, make_desc(Aaddr + aoff, A_LBO, SBO),
-                                         make_desc(Baddr + Cfg::B_TERM_BYTES + ky * 2 * NP * 16, B_LBO, SBO), IDESC, 1u);
+                            if (el) {
+                                umma_f16(d, ah, bh, IDESC, first);
+                                if (TERMS >= 2) umma_f16(d, ah + (uint64_t)(Cfg::A_TERM_BYTES >> 4), bh, IDESC, 1u);
+                                if (TERMS >= 3) umma_f16(d, ah, bh + (uint64_t)(Cfg::B_TERM_BYTES >> 4), IDESC, 1u);
+                            }
                         }
                     }
-                    umma_commit(&op_empty[o]);
-                    TCH_TRACE(4, it);
+                    if (el) umma_commit(&op_empty[o]);
+                    if (lane == 0) TCH_TRACE(4, it);
                 }
-                umma_commit(&acc_full[b]);
+                if (el) umma_commit(&acc_full[b]);
             }
         }
         __syncwarp();
