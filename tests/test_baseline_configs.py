@@ -502,3 +502,34 @@ def test_masked_transfer_tensor_core_stats_vs_oracle(dev, h, w, kind):
     err = maxdiff(out, ref)
     print("masked TC stats %s %dx%d: %.2e" % (kind, h, w, err))
     assert err <= 1e-4
+
+
+@pytest.mark.gpu
+def test_pair_conv_cta_group2_vs_oracle():
+    """conv_pair.cu (tcgen05 cta_group::2, off by default): the 64 -> 256 coupling conv on CTA pairs equals the oracle.
+    The knob is read once per process, hence the subprocess; the profile table proves the pair kernel ran."""
+    import subprocess, sys, os
+    code = r'''
+import torch
+from oracle import vst_oracle as O
+from tests.helpers import cpu_state_dict, fill_biases
+from vstnet_b200 import RevResNet, _lib
+torch.manual_seed(3)
+net = RevResNet(hidden_dim=16, sp_steps=2).eval(); fill_biases(net, 7)
+sd = cpu_state_dict(net); net = net.to("cuda:0")
+for h, w in ((72, 136), (200, 1044), (36, 516)):
+    x = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(h))
+    with torch.no_grad(): zr = O.revnet_forward(sd, x)
+    _lib.profile_enable(True)
+    z = net(x.to("cuda:0")); xr = net.inverse(z)
+    _lib.profile_enable(False); torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    assert any("conv3x3_pair" in k for k in prof), sorted(prof)
+    err = float((z.cpu() - zr).abs().max()); rt = float((xr.cpu() - x).abs().max())
+    assert err <= 1e-3 and rt <= 4e-6, (h, w, err, rt)
+    print("ok", h, w, err, rt)
+'''
+    env = dict(os.environ, VST_TC_PAIR="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr

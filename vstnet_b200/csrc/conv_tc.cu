@@ -582,6 +582,7 @@ int launch_pack_tc_half_weights(const float* w, float* wp, int Cin, int Cout, in
 int launch_conv3x3_tc_half(const ConvArgs& a, cudaStream_t st) {
     VST_REQUIRE(tc_half_eligible(a.Cin, a.Cout, 1), "conv3x3_tc_half: shape %d>%d not eligible", a.Cin, a.Cout);
     VST_REQUIRE(a.Hin == a.Hout && a.Win == a.Wout && a.Hin >= 2 && a.Win >= 2, "conv3x3_tc_half is stride 1, H,W >= 2");
+    if (conv_pair_eligible(a)) return launch_conv3x3_pair(a, st);        // CTA-pair UMMAs (conv_pair.cu)
     const int N = tc_tile_n(a.Cout);
     static int wst = -1;
     if (wst < 0) { const char* e = getenv("VST_TC_WST"); wst = e ? atoi(e) : 1; }

@@ -164,6 +164,8 @@ int launch_conv3x3_tc(const ConvArgs& a, int terms, cudaStream_t st);
 // ... with fp16 split operands: a.in is an H8 tensor, weights packed by launch_pack_tch3_weights (2 terms)
 bool tc_half_eligible(int Cin, int Cout, int stride);
 int launch_pack_tc_half_weights(const float* w, float* wp, int Cin, int Cout, int N, cudaStream_t st);
+bool conv_pair_eligible(const ConvArgs& a);
+int launch_conv3x3_pair(const ConvArgs& a, cudaStream_t st);     // conv_pair.cu: 64 -> 256 on a CTA pair (cta_group::2)
 int launch_conv3x3_tc_half(const ConvArgs& a, cudaStream_t st);
 long long* tc_trace_buffer(int Cin, int Cout, cudaStream_t st);   // developer aid, conv_tc.cu
 
