@@ -155,9 +155,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_chunks = a.Cin / Cfg::KCH;
-    constexpr bool hot = !SQZ;                               // branch-free epilogue; the squeeze modes (SQZ) use generic addressing
-                                                             // in their own instantiation, so their code cannot cost the hot one registers
-    const bool coupled = a.epi == EPI_ADD || a.epi == EPI_SUB;
+    // SQZ (compile time): the instantiation of the stride-2 blocks' coupling modes — the coupling operand is read
+    // through the squeeze addressing (EPI_ADD_SQZ) or the result stored through the unsqueeze addressing
+    // (EPI_SUB_UNSQZ); their address arithmetic cannot cost the plain instantiation registers
+    const bool coupled = a.epi >= EPI_ADD;
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&loaded[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
@@ -316,11 +317,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
         constexpr int NG = N / 8;                                         // cout groups per thread per row
         constexpr int CH = (NG * 4 >= 16) ? 16 : NG * 4;                  // TMEM columns per tcgen05.ld
         const int q = warp & 3, half = warp >> 2;
-        const float sgn = (a.epi == EPI_SUB) ? -1.f : 1.f;
+        const float sgn = (a.epi == EPI_SUB || a.epi == EPI_SUB_UNSQZ) ? -1.f : 1.f;
         const float flo = (a.epi == EPI_RELU) ? 0.f : -INFINITY;
         constexpr float unscale = HALF ? 1.0f / VST_HALF_SCALE : 1.0f;    // H8 operands carry VST_HALF_SCALE * x
         const int H = a.Hout, W = a.Wout, Wp = W + 2;
         const size_t plane = p4_plane_px(H, W);
+        // squeeze modes: cout group g = k * gq + gs is group gs of the un-squeezed tensor [Cout/16][2H+2][2W+2][4] at
+        // pixel (2y + k/2, 2x + k%2)   (models/RevResNet.py:34-43)
+        const bool res_sq = SQZ && a.epi == EPI_ADD_SQZ, out_us = SQZ && a.epi == EPI_SUB_UNSQZ;
+        const int gq = a.Cout >> 4, lgq = __ffs(gq) - 1;
+        const int Hh = 2 * H, Wh = 2 * W, Wph = Wh + 2;
+        const size_t plane_h = p4_plane_px(Hh, Wh);
         uint32_t tcount = 0;
         for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x, ++tcount) {
             const int ct = t % tl.n_ct, rest = t / tl.n_ct;
@@ -329,20 +336,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
             const int x = x0 + q * 32 + lane;
             const bool xin = x < W;
             const int rows = min(R, H - y0);
-            const int g0 = ct * (N / 4) + half * NG;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * Cfg::ACC_COLS + half * (N / 2);
-            if (hot) {
+            // cout groups of this thread: NG consecutive groups (one column half).  (Squeeze modes: giving a thread both
+            // horizontal phases of 8 source groups, so that its consecutive accesses share 32-byte sectors, was measured
+            // 14 % slower than this mapping, where the two phases are fetched by the two column-half warps.)
+            auto g_of = [&](int j) { return ct * (N / 4) + half * NG + j; };
+            auto col_of = [&](int tc) { return half * (N / 2) + tc * CH; };
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * Cfg::ACC_COLS;
+            {
                 const bool lf = (x == 1), rt = (x == W - 2);  // this pixel also feeds border column -1 / W
-                float4* outp = reinterpret_cast<float4*>(a.out) + (size_t)g0 * plane + (size_t)(y0 + 1) * Wp + (x + 1);
-                const float4* resp = reinterpret_cast<const float4*>(a.res) + (size_t)g0 * plane + (size_t)(y0 + 1) * Wp + (x + 1);
+                float4* outp = reinterpret_cast<float4*>(a.out) + (size_t)(y0 + 1) * Wp + (x + 1);
+                const float4* resp = reinterpret_cast<const float4*>(a.res) + (size_t)(y0 + 1) * Wp + (x + 1);
                 float4 res[R][NG];
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
                     for (int j = 0; j < NG; ++j)
-                        res[r][j] = (coupled && xin && r < rows) ? resp[(size_t)j * plane + (size_t)r * Wp]
-                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (coupled && (lane & 7) == 0) {
+                        if (res_sq) {
+                            const int g = g_of(j), k = g >> lgq, gs = g & (gq - 1);
+                            res[r][j] = (xin && r < rows) ? reinterpret_cast<const float4*>(a.res)[(size_t)gs * plane_h + (size_t)(2 * (y0 + r) + (k >> 1) + 1) * Wph +
+                                                                                                    (2 * x + (k & 1) + 1)]
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+                            res[r][j] = (coupled && xin && r < rows) ? resp[(size_t)g_of(j) * plane + (size_t)r * Wp]
+                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                if (!SQZ && coupled && (lane & 7) == 0) {
                     // the coupling operand of this CTA's NEXT tile: pulled HBM -> L2 now (one 128-byte line per 8
                     // lanes), so that its register loads at the top of the next tile find it in L2 — the epilogue
                     // runs behind the UMMAs, so nothing else hides that latency
@@ -368,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                 // combined and stored (a tcgen05.ld takes ~200 cycles while the tensor pipe is busy)
                 constexpr int NCHK = NG * 4 / CH;
                 uint32_t ub[2][CH];
-                tmem_ld_nowait<CH>(trow, ub[0]);                       // warp-collective
+                tmem_ld_nowait<CH>(trow + (uint32_t)col_of(0), ub[0]);        // warp-collective
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     if (r < rows) {                                    // warp-uniform
@@ -384,18 +402,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
 #pragma unroll
                             for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(ub[t & 1][i]);
                             if (t + 1 < R * NCHK && (c0 + CH < NG * 4 || r + 1 < rows))
-                                tmem_ld_nowait<CH>(trow + (uint32_t)(((t + 1) / NCHK) * N + ((t + 1) % NCHK) * CH), ub[(t + 1) & 1]);
+                                tmem_ld_nowait<CH>(trow + (uint32_t)(((t + 1) / NCHK) * N + col_of((t + 1) % NCHK)), ub[(t + 1) & 1]);
                             if (xin) {
 #pragma unroll
                                 for (int jj = 0; jj < CH / 4; ++jj) {
                                     const int j = c0 / 4 + jj;
-                                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * (g0 + j));
+                                    const int g = g_of(j);
+                                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * g);
                                     float4 o = res[r][j];
                                     o.x += fmaxf((v[4 * jj] * unscale + bv.x) * sgn, flo);
                                     o.y += fmaxf((v[4 * jj + 1] * unscale + bv.y) * sgn, flo);
                                     o.z += fmaxf((v[4 * jj + 2] * unscale + bv.z) * sgn, flo);
                                     o.w += fmaxf((v[4 * jj + 3] * unscale + bv.w) * sgn, flo);
-                                    float4* p = outp + (size_t)j * plane + (size_t)r * Wp;
+                                    if (out_us) {
+                                        const int k = g >> lgq, gs = g & (gq - 1);
+                                        p4_store(reinterpret_cast<float4*>(a.out) + (size_t)gs * plane_h, Hh, Wh, 2 * y + (k >> 1), 2 * x + (k & 1), o);
+                                        continue;
+                                    }
+                                    float4* p = outp + (size_t)g * plane + (size_t)r * Wp;
                                     *p = o;
                                     if (lf) p[-2] = o;                 // reflection border, inline and predicated
                                     if (rt) p[2] = o;
@@ -416,44 +440,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_tc_kernel(ConvArgs a, T
                         }
                     }
                     if (tid == 0) TC_TRACE(7, tcount * R + r);
-                }
-            } else {
-                // ---- squeeze / unsqueeze coupling (one launch per pass): generic addressing (conv_epi_res / conv_epi_store),
-                //      but the coupling operand of row r+1 is requested while row r is combined and stored, and that of
-                //      row 0 before the accumulator wait
-                constexpr int NGH = N / 8;                                // cout groups per thread per row
-                float4 rr[2][NGH];
-#pragma unroll
-                for (int j = 0; j < NGH; ++j)
-                    rr[0][j] = (xin && rows > 0) ? conv_epi_res(a, g0 + j, y0, x) : make_float4(0.f, 0.f, 0.f, 0.f);
-                mbar_wait(&acc_full[b], (tcount >> 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (r < rows) {                                       // warp-uniform
-                        const int y = y0 + r;
-                        if (r + 1 < R) {
-#pragma unroll
-                            for (int j = 0; j < NGH; ++j)
-                                rr[(r + 1) & 1][j] = (xin && r + 1 < rows) ? conv_epi_res(a, g0 + j, y + 1, x) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int c0 = 0; c0 < N / 2; c0 += CH) {
-                            float v[CH];
-                            tmem_ld<CH>(trow + (uint32_t)(r * N + c0), v);
-                            if (xin) {
-#pragma unroll
-                                for (int jj = 0; jj < CH / 4; ++jj) {
-                                    const int g = g0 + c0 / 4 + jj;
-                                    const float4 bv = *reinterpret_cast<const float4*>(bias_s + 4 * g);
-                                    conv_epi_store(a, g, y, x,
-                                                   make_float4(v[4 * jj] * unscale + bv.x, v[4 * jj + 1] * unscale + bv.y,
-                                                               v[4 * jj + 2] * unscale + bv.z, v[4 * jj + 3] * unscale + bv.w),
-                                                   rr[r & 1][c0 / 4 + jj]);
-                                }
-                            }
-                        }
-                    }
                 }
             }
             tc_fence_before();
@@ -506,7 +492,7 @@ static int launch_tc_cfg2(const ConvArgs& a, cudaStream_t st) {
     int grid = std::min(tl.n_tiles, num_sms());
     if (WST) grid -= grid % tl.n_ct;             // a CTA's tiles must all have the same cout tile
     char cls[40];
-    snprintf(cls, sizeof(cls), HALF ? "conv3x3_tcH%d %d>%d" : "conv3x3_tc%d %d>%d", TERMS, a.Cin, a.Cout);
+    snprintf(cls, sizeof(cls), HALF ? "conv3x3_tcH%d %d>%d%s" : "conv3x3_tc%d %d>%d%s", TERMS, a.Cin, a.Cout, SQZ ? " sqz" : "");
     const double px = (double)a.Hout * a.Wout;
     const bool coupled = a.epi >= EPI_ADD;
     ProfScope prof(st, cls, 2.0 * 9 * a.Cin * a.Cout * px,
@@ -586,8 +572,8 @@ int launch_conv3x3_tc_half(const ConvArgs& a, cudaStream_t st) {
     const int N = tc_tile_n(a.Cout);
     static int wst = -1;
     if (wst < 0) { const char* e = getenv("VST_TC_WST"); wst = e ? atoi(e) : 1; }
-    if (N == 128 && wst && a.Cin == 64 && a.epi <= EPI_SUB && (a.Cout / N) <= num_sms())
-        return launch_tc_cfg2<128, 2, 2, true, false, true>(a, st);      // resident weights (the 64 -> 256 coupling convs)
+    if (N == 128 && wst && a.Cin == 64 && (a.Cout / N) <= num_sms())      // resident weights (the 64 -> 256 coupling convs)
+        return a.epi <= EPI_SUB ? launch_tc_cfg2<128, 2, 2, true, false, true>(a, st) : launch_tc_cfg2<128, 2, 2, true, true, true>(a, st);
     if (N == 128) return launch_tc_cfg<128, 2, 2, true>(a, st);
     if (N == 64) return launch_tc_cfg<64, 4, 2, true>(a, st);
     return launch_tc_cfg<16, 4, 2, true>(a, st);
