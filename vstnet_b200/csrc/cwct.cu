@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const float* __restrict__ fe
 // Tile = one sub-position x PX consecutive interior pixels; same thread tile (8 channels x 4 pixels, FFMA2) as above.
 // ------------------------------------------------------------------------------------------
 template <int CP>
-__global__ void __launch_bounds__(256) apply_state_kernel(float* __restrict__ x1, float* __restrict__ x2, int Ch, int h, int w,
+__global__ void __launch_bounds__(256, CP == 32 ? 4 : 1) apply_state_kernel(float* __restrict__ x1, float* __restrict__ x2, int Ch, int h, int w,
                                                           const float* __restrict__ T, const float* __restrict__ mu,
                                                           const float* __restrict__ beta, const int* __restrict__ valid,
                                                           int tiles_per_sub, int n_tiles) {
@@ -750,10 +750,11 @@ __global__ void __launch_bounds__(256) apply_state_kernel(float* __restrict__ x1
             for (int it = 0; it < NIT; ++it)
                 v[it] = (px < npx) ? src[(size_t)(it * (256 / PX) + gq) * plane] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int it = 0; it < NIT; ++it) {
+            for (int it = 0; it < NIT; ++it) {                 // staged centred: x - mu
                 const int g = it * (256 / PX) + gq;
-                xs[(4 * g + 0) * PX + px] = v[it].x; xs[(4 * g + 1) * PX + px] = v[it].y;
-                xs[(4 * g + 2) * PX + px] = v[it].z; xs[(4 * g + 3) * PX + px] = v[it].w;
+                const float4 m4 = *reinterpret_cast<const float4*>(mu_s + 4 * g);
+                xs[(4 * g + 0) * PX + px] = v[it].x - m4.x; xs[(4 * g + 1) * PX + px] = v[it].y - m4.y;
+                xs[(4 * g + 2) * PX + px] = v[it].z - m4.z; xs[(4 * g + 3) * PX + px] = v[it].w - m4.w;
             }
         }
         __syncthreads();
@@ -769,8 +770,7 @@ __global__ void __launch_bounds__(256) apply_state_kernel(float* __restrict__ x1
             const float* xr = xs + k * PX + pg;
             const float4 t0 = *reinterpret_cast<const float4*>(Tt + k * CP + cg * 8);
             const float4 t1 = *reinterpret_cast<const float4*>(Tt + k * CP + cg * 8 + 4);
-            const float m = mu_s[k];
-            const float xv[4] = {xr[0] - m, xr[NPG] - m, xr[2 * NPG] - m, xr[3 * NPG] - m};
+            const float xv[4] = {xr[0], xr[NPG], xr[2 * NPG], xr[3 * NPG]};
             const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
