@@ -50,9 +50,18 @@ struct TchCfg {
     static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
     static constexpr int AUX_BYTES = 2048;                          // barriers (1 KB) + bias (1 KB)
-    static constexpr int NO = 3;                                    // operand ring depth
+    // operand ring depth.  The chunk's weights (18 KB at NC = 64) ride in the operand slot and take 3-4 k cycles to land,
+    // like the raw box: with three slots the few-chunk R = 1 convs ran at fill latency / 3 = ~1.2 k cycles per chunk
+    static constexpr int NO = (R == 1 && NC == 64 && TERMS <= 2) ? 5 : 3;
+    // converter teams.  A chunk's conversion is a latency chain (LDS -> cvt -> STS, ~1 k cycles with the barrier
+    // traffic around it) however few items a thread has; the few-chunk R = 1 convs were paced by it (role trace: ~1.2 k
+    // cycles per chunk vs ~400 of UMMAs).  Two teams of four warps convert alternate chunks concurrently.
+    static constexpr int TEAMS = (R == 1) ? 2 : 1;
+    // raw ring depth (TMA boxes in flight).  A box takes 3-4 k cycles to land under load (role trace); the few-chunk
+    // R = 1 convs spend only ~400 cycles of UMMAs per chunk, so four boxes in flight paced them at ~1.2 k cycles per chunk
+    static constexpr int NR_MAX = (R == 1) ? 8 : 4;
     static constexpr int NR_FIT = (226 * 1024 - AUX_BYTES - NO * OP_BYTES) / RAW_BYTES;
-    static constexpr int NR = NR_FIT > 4 ? 4 : NR_FIT;              // raw ring depth
+    static constexpr int NR = NR_FIT > NR_MAX ? NR_MAX : NR_FIT;
     static constexpr size_t SMEM = (size_t)NR * RAW_BYTES + (size_t)NO * OP_BYTES + AUX_BYTES + 128;
     static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NP % 16 == 0 && NP <= 256, "UMMA M=128 needs N % 16 == 0, N <= 256");
@@ -160,13 +169,13 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     uint8_t* raw_base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // by offset: keeps the __shared__ address space (LDS / STS)
     uint8_t* op_base = raw_base + (size_t)NR * Cfg::RAW_BYTES;
     uint64_t* bars = (uint64_t*)(op_base + (size_t)NO * Cfg::OP_BYTES);
-    uint64_t* raw_full = bars;                  // [NR]    activation producer arrive.expect_tx + TMA bytes
-    uint64_t* raw_empty = bars + 4;             // [NR]    converter threads
-    uint64_t* op_ready = bars + 8;              // [NO]    128 converter threads + weight producer arrive.expect_tx + TMA bytes
-    uint64_t* op_empty = bars + 12;             // [NO]    tcgen05.commit
-    uint64_t* acc_full = bars + 16;             // [NACC]  tcgen05.commit
-    uint64_t* acc_empty = bars + 18;            // [NACC]  256 epilogue threads
-    uint32_t* tmem_slot = (uint32_t*)(bars + 20);
+    uint64_t* raw_full = bars;                  // [NR <= 8]  activation producer arrive.expect_tx + TMA bytes
+    uint64_t* raw_empty = bars + 8;             // [NR <= 8]  converter threads
+    uint64_t* op_ready = bars + 16;             // [NO <= 8]  converter threads + weight producer arrive.expect_tx + TMA bytes
+    uint64_t* op_empty = bars + 24;             // [NO <= 8]  tcgen05.commit
+    uint64_t* acc_full = bars + 32;             // [NACC]  tcgen05.commit
+    uint64_t* acc_empty = bars + 34;            // [NACC]  256 epilogue threads
+    uint32_t* tmem_slot = (uint32_t*)(bars + 36);
     float* bias_s = (float*)((uint8_t*)bars + 1024);
     for (int i = threadIdx.x; i < a.Cout && i < 256; i += blockDim.x) bias_s[i] = __ldg(a.bias + i);
 
@@ -174,8 +183,8 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     const int n_chunks = a.Cin / 16;
 
     if (tid == 0) {
-        for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 32 * TCH_NCW); }
-        for (int s = 0; s < NO; ++s) { mbar_init(&op_ready[s], 32 * TCH_NCW + 1); mbar_init(&op_empty[s], 1); }
+        for (int s = 0; s < NR; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 32 * TCH_NCW / Cfg::TEAMS); }
+        for (int s = 0; s < NO; ++s) { mbar_init(&op_ready[s], 32 * TCH_NCW / Cfg::TEAMS + 1); mbar_init(&op_empty[s], 1); }
         for (int b = 0; b < NACC; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
         fence_barrier_init();
     }
@@ -275,20 +284,22 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
     } else if (warp >= 8 && warp < 8 + TCH_NCW) {
         // ================= converters: raw fp32 -> fp16 hi / lo in the K-major operand layout =================
         // one item = 8 channels (two P4 groups) of one pixel: 32 bytes in, 16 (hi) + 16 (lo) bytes out
-        const int ctid = tid - 256;
+        constexpr int TEAMS = Cfg::TEAMS, TEAM_THREADS = 32 * TCH_NCW / TEAMS;
+        const int team = (tid - 256) / TEAM_THREADS, ctid = (tid - 256) % TEAM_THREADS;
         uint32_t it = 0;
         uint32_t hmax = 0u;                    // fp16 range guard (tc_ptx.cuh)
         for (int t = blockIdx.x; t < tl.n_tiles; t += gridDim.x) {
             for (int c = 0; c < n_chunks; ++c, ++it) {
+                if (TEAMS > 1 && (int)(it % TEAMS) != team) continue;      // the other team's chunk
                 const int s = it % NR, o = it % NO;
                 mbar_wait(&raw_full[s], (it / NR) & 1);
                 mbar_wait(&op_empty[o], ((it / NO) & 1) ^ 1);          // the UMMAs that read this slot are done
-                if (ctid == 0) TCH_TRACE(1, it);
+                if (tid == 256) TCH_TRACE(1, it);
                 const float4* raw = reinterpret_cast<const float4*>(raw_base + (size_t)s * Cfg::RAW_BYTES);
                 uint4* hi = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES);
                 uint4* lo = reinterpret_cast<uint4*>(op_base + (size_t)o * Cfg::OP_BYTES + Cfg::A_TERM_BYTES);
 #pragma unroll 4
-                for (int i = ctid; i < 2 * ROWS * WIN; i += 32 * TCH_NCW) {
+                for (int i = ctid; i < 2 * ROWS * WIN; i += TEAM_THREADS) {
                     const int kh = i / (ROWS * WIN), rp = i - kh * (ROWS * WIN);    // k-half, (image row, pixel): same index in RAW
                     const float4 u = raw[(2 * kh) * (ROWS * WIN) + rp];
                     const float4 v = raw[(2 * kh + 1) * (ROWS * WIN) + rp];
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                 fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core
                 mbar_arrive(&op_ready[o]);
                 mbar_arrive(&raw_empty[s]);
-                if (ctid == 0) TCH_TRACE(2, it);
+                if (tid == 256) TCH_TRACE(2, it);
             }
         }
         range_report(hmax, a.status);
