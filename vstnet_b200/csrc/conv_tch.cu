@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
             if (tid == 0) TCH_TRACE(6, tcount);
             // out[m] = D[m-1][kx=0] + D[m][kx=1] + D[m+1][kx=2], all within the warp
             const bool lf = xok && (x == 1), rt = xok && (x == W - 2);
+            const int r_last = min(R, (H - y0 + 3) / 4) - 1;        // last block of this tile with rows inside the image
 #pragma unroll 1
             for (int r = 0; r < R; ++r) {
                 const int y = y0 + 4 * r + q;
@@ -361,6 +362,12 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                     float v0[CH], v1[CH], v2[CH];
                     tmem_ld3<CH>(trow + (uint32_t)(r * NP + 0 * NC + c0), v0, trow + (uint32_t)(r * NP + 1 * NC + c0), v1,
                                  trow + (uint32_t)(r * NP + 2 * NC + c0), v2);
+                    if (r == r_last && c0 + CH >= HC) {
+                        // the tile's last TMEM read has completed: the accumulator goes back to the issuer now, the fold,
+                        // conversion and stores below run beside the next tile's UMMAs
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[b]);
+                    }
                     if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 0);
                     const int cb = half * HC + c0;                  // first cout of this chunk (within the tile)
 #pragma unroll
@@ -443,8 +450,6 @@ __global__ void __launch_bounds__(TCH_THREADS, 1) conv3x3_tch_kernel(ConvArgs a,
                     if (tid == 0 && tcount == 1) TCH_TRACE(7, 16 + (r * (HC / CH) + c0 / CH) * 3 + 2);
                 }
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[b]);
             if (tid == 0) TCH_TRACE(7, 2 * tcount + 1);
         }
         if (SPLIT) range_report(hmax, a.status);
