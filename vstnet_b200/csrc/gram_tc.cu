@@ -113,8 +113,9 @@ gram_tc_kernel(GramTcArgs a, const __grid_constant__ CUtensorMap tm0, const __gr
                 } else {
                     // box {KT pixels x 4 floats, 1 row, 32 groups} of the half-state that holds sub-position block jb
                     // x-block fastest: consecutive boxes continue the same 32 DRAM streams.  Knock-out builds (no converter
-                    // work / no UMMAs / neither): 0.084 / 0.102 / 0.079 ms against 0.119 ms — the bare TMA stream of
-                    // 512-byte runs over 32 planes is the floor (3.35 TB/s); ring depth 8 and this order change it by < 3 %
+                    // work / no UMMAs / neither): 0.084 / 0.102 / 0.079 ms against 0.119 ms; ring depth 8 and this order
+                    // change it by < 3 %.  (tools/ubench/tma_stream.cu: the same boxes with no consumer warps at all take
+                    // 0.058 ms, whatever the box shape — the plane layout is not what limits the stream.)
                     const int xb = st % a.n_xb, r = st / a.n_xb;
                     const int jb = r % a.n_jb, y = r / a.n_jb;
                     const int g0 = jb * 32;                                 // first state group of the block
