@@ -27,8 +27,10 @@ __device__ __forceinline__ void tma3(void* dst, const CUtensorMap* tm, int c0, i
 constexpr int BOX_BYTES = 16384;
 struct Geo { int b0, b1, b2; int n0, n1, n2; int stages; };   // box dims (elements / rows / planes), boxes per dimension
 
+// wr > 0: every wr-th box is also written back (a 16 KB bulk store to a linear buffer): wr = 2 is the 2 : 1 read : write mix
+// of a coupling block (read x, read the coupling operand, write the result)
 template <int NR>
-__global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ CUtensorMap tm, Geo g, int stages_per_cta) {
+__global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ CUtensorMap tm, Geo g, int stages_per_cta, float* out, int wr) {
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t* ring = sm + ((1024u - (s32(sm) & 1023u)) & 1023u);
     __shared__ uint64_t full[NR], empty[NR];
@@ -50,6 +52,12 @@ __global__ void __launch_bounds__(64, 1) stream_kernel(const __grid_constant__ C
         for (int st = st0, i = 0; st < st1; ++st, ++i) {
             const int s = i % NR;
             mbar_wait(&full[s], (i / NR) & 1);
+            if (wr > 0 && i % wr == wr - 1) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + (size_t)st * (BOX_BYTES / 4)),
+                             "r"(s32(ring + (size_t)s * BOX_BYTES)), "n"(BOX_BYTES) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
             mbar_arrive(&empty[s]);
         }
     }
@@ -66,6 +74,7 @@ int main() {
     const size_t plane = (size_t)H * W * 4, total = (size_t)G * plane;
     float* buf; CK(cudaMalloc(&buf, total * 4 + (1 << 20))); CK(cudaMemset(buf, 0, total * 4));
     float* flush; CK(cudaMalloc(&flush, 256 << 20));
+    float* out; CK(cudaMalloc(&out, total * 4 + (1 << 20)));
     int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     struct V { const char* name; int rank3; cuuint64_t d[3]; cuuint64_t s[2]; cuuint32_t b[3]; } vs[] = {
         {"planes 512 B x 32 groups ", 1, {(cuuint64_t)W * 4, (cuuint64_t)H, G}, {(cuuint64_t)W * 16, plane * 4}, {128, 1, 32}},
@@ -85,7 +94,8 @@ int main() {
         g.n0 = (int)(v.d[0] / v.b[0]); g.n1 = (int)(v.d[1] / v.b[1]); g.n2 = (int)(v.d[2] / v.b[2]);
         g.stages = g.n0 * g.n1 * g.n2;
         const int spc = (g.stages + sms - 1) / sms;
-        for (int nr : {6, 12}) {
+        for (int cfg = 0; cfg < 3; ++cfg) {
+            const int nr = cfg == 1 ? 12 : 6, wr = cfg == 2 ? 2 : 0;
             auto kern = nr == 6 ? stream_kernel<6> : stream_kernel<12>;
             const size_t smem = (size_t)nr * BOX_BYTES + 1024;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -94,14 +104,15 @@ int main() {
             for (int rep = 0; rep < 5; ++rep) {
                 CK(cudaMemsetAsync(flush, rep, 256 << 20));          // evict the tensor from L2
                 cudaEventRecord(e0);
-                kern<<<sms, 64, smem>>>(tm, g, spc);
+                kern<<<sms, 64, smem>>>(tm, g, spc, out, wr);
                 cudaEventRecord(e1);
                 CK(cudaEventSynchronize(e1));
                 float ms; cudaEventElapsedTime(&ms, e0, e1);
                 if (ms < best) best = ms;
             }
-            const double bytes = (double)g.stages * BOX_BYTES;
-            printf("%s ring %2d x 16 KB: %.3f ms  %.0f MB  %.2f TB/s\n", v.name, nr, best, bytes / 1e6, bytes / best / 1e9);
+            const double bytes = (double)g.stages * BOX_BYTES * (wr ? 1.0 + 1.0 / wr : 1.0);
+            printf("%s ring %2d x 16 KB%s: %.3f ms  %.0f MB  %.2f TB/s\n", v.name, nr, wr ? ", every 2nd box written back" : "", best, bytes / 1e6,
+                   bytes / best / 1e9);
         }
     }
     return 0;
